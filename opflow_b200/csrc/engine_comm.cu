@@ -1,0 +1,217 @@
+// engine_comm.cu -- one-process-per-GPU communicator (NCCL over NVLink5/NVSwitch) and the halo exchange that replaces
+// the MPI branch of updatePaddingImpl_final (CartesianField.hpp:630-768: serial pack -> MPI_Isend/Irecv -> Waitall ->
+// serial unpack) and the MPI_Allgather of globalReduce (RangeFor.hpp:125-135).
+// NCCL is dlopen'ed so single-GPU use has no NCCL dependency.
+#include "engine.hpp"
+#include <algorithm>
+#include <dlfcn.h>
+
+namespace {
+    typedef struct ncclComm* ncclComm_t;
+    typedef struct { char internal[128]; } ncclUniqueId;
+    typedef int ncclResult_t;
+    enum { ncclFloat64 = 8 };
+    enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+
+    struct Nccl {
+        void* h = nullptr;
+        ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+        ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+        ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+        ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*GroupStart)() = nullptr;
+        ncclResult_t (*GroupEnd)() = nullptr;
+        const char* (*GetErrorString)(ncclResult_t) = nullptr;
+        ncclComm_t comm = nullptr;
+        int rank = 0, size = 1;
+        double* dbuf = nullptr;
+    };
+    Nccl& nc() {
+        static Nccl n;
+        return n;
+    }
+    int load_nccl() {
+        Nccl& n = nc();
+        if (n.h) return OPF_OK;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.h) break;
+        }
+        if (!n.h) return opfe::fail(OPF_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define OPF_SYM(field, sym)                                                                                            \
+    *(void**) (&n.field) = dlsym(n.h, sym);                                                                            \
+    if (!n.field) return opfe::fail(OPF_ERR_COMM, "libnccl lacks %s", sym);
+        OPF_SYM(GetUniqueId, "ncclGetUniqueId")
+        OPF_SYM(CommInitRank, "ncclCommInitRank")
+        OPF_SYM(CommDestroy, "ncclCommDestroy")
+        OPF_SYM(Send, "ncclSend")
+        OPF_SYM(Recv, "ncclRecv")
+        OPF_SYM(AllReduce, "ncclAllReduce")
+        OPF_SYM(GroupStart, "ncclGroupStart")
+        OPF_SYM(GroupEnd, "ncclGroupEnd")
+        OPF_SYM(GetErrorString, "ncclGetErrorString")
+#undef OPF_SYM
+        return OPF_OK;
+    }
+#define OPF_NCCL(call)                                                                                                 \
+    do {                                                                                                               \
+        ncclResult_t r__ = (call);                                                                                     \
+        if (r__ != 0) return opfe::fail(OPF_ERR_COMM, "%s: %s", #call, nc().GetErrorString(r__));                     \
+    } while (0)
+
+    // pack / unpack one box between the pitched field storage and a dense staging buffer (K6)
+    __global__ void __launch_bounds__(256) box_copy_kernel(double* field, long long s1, long long s2, double* stage,
+                                                           opf::LaunchRange r, int to_stage) {
+        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
+        const long long total = n0 * n1 * n2;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            const long long o = (r.lo[0] + t % n0) + (r.lo[1] + (t / n0) % n1) * s1 + (r.lo[2] + t / (n0 * n1)) * s2;
+            if (to_stage) stage[t] = field[o];
+            else
+                field[o] = stage[t];
+        }
+    }
+
+    int inverse_code(int code, int dim) {
+        int out = 0, p = 1;
+        for (int d = 0; d < dim; ++d) {
+            int dir = (code / p) % 3;
+            if (dir == 1) dir = 2;
+            else if (dir == 2)
+                dir = 1;
+            out += dir * p;
+            p *= 3;
+        }
+        return out;
+    }
+}// namespace
+
+namespace opfe {
+    bool comm_active() { return nc().comm != nullptr; }
+
+    int halo_exchange(opf_field_s* f) {
+        Nccl& n = nc();
+        if (f->neighbors.empty()) return OPF_OK;
+        if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
+        Context& c = ctx();
+        const int nn = (int) f->neighbors.size();
+        // staging layout: sends in neighbour order, recvs in neighbour order
+        std::vector<long long> soff(nn + 1, 0), roff(nn + 1, 0);
+        for (int i = 0; i < nn; ++i) {
+            soff[i + 1] = soff[i] + f->neighbors[i].send.count();
+            roff[i + 1] = roff[i] + std::max<long long>(0, f->neighbors[i].recv.count());
+        }
+        const long long need = std::max(soff[nn], roff[nn]);
+        if (need > f->halo_elems) {
+            if (f->halo_send) cudaFree(f->halo_send);
+            if (f->halo_recv) cudaFree(f->halo_recv);
+            OPF_CUDA(cudaMalloc(&f->halo_send, sizeof(double) * need));
+            OPF_CUDA(cudaMalloc(&f->halo_recv, sizeof(double) * need));
+            f->halo_elems = need;
+        }
+        double* fb = f->biased(f->cur);
+        auto lr = [](const Range& r) {
+            opf::LaunchRange o;
+            for (int d = 0; d < 3; ++d) {
+                o.lo[d] = r.start[d];
+                o.hi[d] = r.end[d];
+            }
+            return o;
+        };
+        for (int i = 0; i < nn; ++i) {
+            const long long cnt = soff[i + 1] - soff[i];
+            const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
+            box_copy_kernel<<<blocks, 256, 0, c.stream>>>(fb, f->pitch1, f->pitch2, f->halo_send + soff[i], lr(f->neighbors[i].send), 1);
+            c.launches++;
+        }
+        OPF_CUDA(cudaGetLastError());
+        // message order per peer: sender's shift code ascending on both sides (the reference matches by tag =
+        // hash(recv range), CartesianField.hpp:689-716)
+        std::vector<int> sorder(nn), rorder(nn);
+        for (int i = 0; i < nn; ++i) sorder[i] = rorder[i] = i;
+        std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) { return f->neighbors[a].code < f->neighbors[b].code; });
+        std::stable_sort(rorder.begin(), rorder.end(), [&](int a, int b) {
+            return inverse_code(f->neighbors[a].code, f->dim) < inverse_code(f->neighbors[b].code, f->dim);
+        });
+        OPF_NCCL(n.GroupStart());
+        for (int k = 0; k < nn; ++k) {
+            const int i = sorder[k];
+            OPF_NCCL(n.Send(f->halo_send + soff[i], (size_t) (soff[i + 1] - soff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, c.stream));
+        }
+        for (int k = 0; k < nn; ++k) {
+            const int i = rorder[k];
+            if (roff[i + 1] - roff[i] > 0)
+                OPF_NCCL(n.Recv(f->halo_recv + roff[i], (size_t) (roff[i + 1] - roff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, c.stream));
+        }
+        OPF_NCCL(n.GroupEnd());
+        for (int i = 0; i < nn; ++i) {
+            const long long cnt = roff[i + 1] - roff[i];
+            if (cnt <= 0) continue;
+            const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
+            box_copy_kernel<<<blocks, 256, 0, c.stream>>>(fb, f->pitch1, f->pitch2, f->halo_recv + roff[i], lr(f->neighbors[i].recv), 0);
+            c.launches++;
+        }
+        OPF_CUDA(cudaGetLastError());
+        return OPF_OK;
+    }
+}// namespace opfe
+
+extern "C" {
+
+int opf_comm_unique_id(void* id128) {
+    if (!id128) return opfe::fail(OPF_ERR_INVALID, "null id");
+    if (int rc = load_nccl()) return rc;
+    ncclUniqueId id;
+    OPF_NCCL(nc().GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return OPF_OK;
+}
+
+int opf_comm_init(int rank, int n_ranks, const void* id128) {
+    if (!id128 || rank < 0 || rank >= n_ranks) return opfe::fail(OPF_ERR_INVALID, "bad arguments");
+    if (int rc = opfe::require_device()) return rc;
+    if (int rc = load_nccl()) return rc;
+    Nccl& n = nc();
+    if (n.comm) return OPF_OK;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    OPF_NCCL(n.CommInitRank(&n.comm, n_ranks, id, rank));
+    n.rank = rank;
+    n.size = n_ranks;
+    OPF_CUDA(cudaMalloc(&n.dbuf, sizeof(double) * 64));
+    return OPF_OK;
+}
+int opf_comm_rank(void) { return nc().rank; }
+int opf_comm_size(void) { return nc().size; }
+
+int opf_comm_allreduce(double* values, int cnt, int rop) {
+    Nccl& n = nc();
+    if (cnt <= 0 || cnt > 64 || !values) return opfe::fail(OPF_ERR_INVALID, "allreduce count must be 1..64");
+    if (!n.comm) return OPF_OK;// single process: identity
+    opfe::Context& c = opfe::ctx();
+    const int op = rop == OPF_RED_MAX || rop == OPF_RED_ABSMAX ? ncclMax : (rop == OPF_RED_MIN ? ncclMin : ncclSum);
+    OPF_CUDA(cudaMemcpyAsync(n.dbuf, values, sizeof(double) * cnt, cudaMemcpyHostToDevice, c.stream));
+    OPF_NCCL(n.AllReduce(n.dbuf, n.dbuf, (size_t) cnt, ncclFloat64, op, n.comm, c.stream));
+    OPF_CUDA(cudaMemcpyAsync(values, n.dbuf, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c.stream));
+    OPF_CUDA(cudaStreamSynchronize(c.stream));
+    return OPF_OK;
+}
+
+int opf_comm_finalize(void) {
+    Nccl& n = nc();
+    if (n.comm) {
+        cudaStreamSynchronize(opfe::ctx().stream);
+        n.CommDestroy(n.comm);
+        n.comm = nullptr;
+        cudaFree(n.dbuf);
+        n.dbuf = nullptr;
+    }
+    n.rank = 0;
+    n.size = 1;
+    return OPF_OK;
+}
+
+}// extern "C"

@@ -1,0 +1,579 @@
+// engine_expr.cu -- expression IR (parsed from the functor-type signature), Expr::prepare() range algebra,
+// FieldAssigner::assign and rangeReduce on the device.
+//   reference: src/Core/Expr/Expression.hpp:99-105 (prepare / contains), every Op::prepare (cited per node below),
+//              src/Core/Loops/FieldAssigner.hpp:26-86, src/Core/Loops/RangeFor.hpp:87-121.
+#include "engine.hpp"
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
+namespace opfe {
+
+    enum Kind {
+        K_F, K_S,
+        K_ADD, K_SUB, K_MUL, K_DIV, K_MIN, K_MAX, K_POW, K_LT, K_LE, K_GT, K_GE, K_EQ, K_NE, K_AND, K_OR,
+        K_NEG, K_POS, K_NOT, K_SQRT, K_ABS, K_EXP, K_LOG, K_SIN, K_COS, K_TAN, K_TANH, K_POW2,
+        K_COND,
+        K_D2C, K_D1C, K_D1DN, K_D1UP, K_WENODN, K_WENOUP, K_INTPC2N, K_INTPN2C
+    };
+    struct KindInfo {
+        const char* name;
+        int kind, nchild;
+        bool has_axis;
+    };
+    static const KindInfo kinds[] = {
+            {"F", K_F, 0, false},         {"S", K_S, 0, false},         {"Add", K_ADD, 2, false},     {"Sub", K_SUB, 2, false},
+            {"Mul", K_MUL, 2, false},     {"Div", K_DIV, 2, false},     {"Min", K_MIN, 2, false},     {"Max", K_MAX, 2, false},
+            {"Pow", K_POW, 2, false},     {"Lt", K_LT, 2, false},       {"Le", K_LE, 2, false},       {"Gt", K_GT, 2, false},
+            {"Ge", K_GE, 2, false},       {"Eq", K_EQ, 2, false},       {"Ne", K_NE, 2, false},       {"And", K_AND, 2, false},
+            {"Or", K_OR, 2, false},       {"Neg", K_NEG, 1, false},     {"Pos", K_POS, 1, false},     {"Not", K_NOT, 1, false},
+            {"Sqrt", K_SQRT, 1, false},   {"Abs", K_ABS, 1, false},     {"Exp", K_EXP, 1, false},     {"Log", K_LOG, 1, false},
+            {"Sin", K_SIN, 1, false},     {"Cos", K_COS, 1, false},     {"Tan", K_TAN, 1, false},     {"Tanh", K_TANH, 1, false},
+            {"Pow2", K_POW2, 1, false},   {"Cond", K_COND, 3, false},   {"D2C", K_D2C, 1, true},      {"D1C", K_D1C, 1, true},
+            {"D1Dn", K_D1DN, 1, true},    {"D1Up", K_D1UP, 1, true},    {"WenoDn", K_WENODN, 1, true}, {"WenoUp", K_WENOUP, 1, true},
+            {"IntpC2N", K_INTPC2N, 1, true}, {"IntpN2C", K_INTPN2C, 1, true}};
+
+    struct Node {
+        int kind = 0, axis = -1, leaf = -1, nchild = 0;
+        int child[3] = {-1, -1, -1};
+        // prepared properties
+        bool scalar = false;
+        int loc[D3] = {0, 0, 0};
+        Range acc, local, logical;
+        const opf_field_s* src = nullptr;// field whose props were inherited (mesh etc.)
+    };
+    struct Tree {
+        std::vector<Node> nodes;// preorder: node index == device-side B
+        int nfields = 0, nscalars = 0;
+    };
+
+    struct Parser {
+        const char* s;
+        size_t pos = 0;
+        std::string err;
+        void ws() {
+            while (s[pos] == ' ') ++pos;
+        }
+        bool parse_int(int& v) {
+            ws();
+            bool neg = false;
+            if (s[pos] == '-') {
+                neg = true;
+                ++pos;
+            }
+            if (s[pos] < '0' || s[pos] > '9') return false;
+            v = 0;
+            while (s[pos] >= '0' && s[pos] <= '9') v = v * 10 + (s[pos++] - '0');
+            if (neg) v = -v;
+            return true;
+        }
+        int parse_node(Tree& t) {
+            ws();
+            size_t b = pos;
+            while ((s[pos] >= 'A' && s[pos] <= 'Z') || (s[pos] >= 'a' && s[pos] <= 'z') || (s[pos] >= '0' && s[pos] <= '9')) ++pos;
+            std::string name(s + b, pos - b);
+            const KindInfo* ki = nullptr;
+            for (const auto& k : kinds)
+                if (name == k.name) ki = &k;
+            if (!ki) {
+                err = "unknown node '" + name + "'";
+                return -1;
+            }
+            ws();
+            if (s[pos] != '<') {
+                err = "expected '<' after " + name;
+                return -1;
+            }
+            ++pos;
+            const int me = (int) t.nodes.size();
+            t.nodes.emplace_back();
+            t.nodes[me].kind = ki->kind;
+            t.nodes[me].nchild = ki->nchild;
+            if (ki->kind == K_F || ki->kind == K_S) {
+                int v;
+                if (!parse_int(v) || v < 0) {
+                    err = "bad leaf index";
+                    return -1;
+                }
+                t.nodes[me].leaf = v;
+                t.nodes[me].scalar = ki->kind == K_S;
+                if (ki->kind == K_F) t.nfields = std::max(t.nfields, v + 1);
+                else
+                    t.nscalars = std::max(t.nscalars, v + 1);
+            } else {
+                if (ki->has_axis) {
+                    int v;
+                    if (!parse_int(v) || v < 0 || v >= D3) {
+                        err = "bad axis";
+                        return -1;
+                    }
+                    t.nodes[me].axis = v;
+                    ws();
+                    if (s[pos] != ',') {
+                        err = "expected ','";
+                        return -1;
+                    }
+                    ++pos;
+                }
+                for (int c = 0; c < ki->nchild; ++c) {
+                    if (c) {
+                        ws();
+                        if (s[pos] != ',') {
+                            err = "expected ',' in " + name;
+                            return -1;
+                        }
+                        ++pos;
+                    }
+                    int ch = parse_node(t);
+                    if (ch < 0) return -1;
+                    t.nodes[me].child[c] = ch;
+                }
+            }
+            ws();
+            if (s[pos] != '>') {
+                err = "expected '>' closing " + name;
+                return -1;
+            }
+            ++pos;
+            return me;
+        }
+    };
+
+    static int parse_signature(const char* sig, Tree& t) {
+        Parser p{sig};
+        if (p.parse_node(t) != 0) return fail(OPF_ERR_INVALID, "signature '%s': %s", sig, p.err.c_str());
+        p.ws();
+        if (sig[p.pos] != 0) return fail(OPF_ERR_INVALID, "signature '%s': trailing characters", sig);
+        if ((int) t.nodes.size() > OPF_MAX_NODES) return fail(OPF_ERR_UNSUPPORTED, "expression has %zu nodes (max %d)", t.nodes.size(), OPF_MAX_NODES);
+        if (t.nfields > OPF_MAX_FIELDS || t.nscalars > OPF_MAX_SCALARS) return fail(OPF_ERR_UNSUPPORTED, "too many leaves");
+        return OPF_OK;
+    }
+
+    static void inherit(Node& n, const Node& a) {
+        n.scalar = a.scalar;
+        for (int d = 0; d < D3; ++d) n.loc[d] = a.loc[d];
+        n.acc = a.acc;
+        n.local = a.local;
+        n.logical = a.logical;
+        n.src = a.src;
+    }
+
+    // post-order prepare (Expression.hpp:99-103)
+    static int prepare_node(Tree& t, int id, const opf_field_t* fields, int nfields) {
+        Node& n = t.nodes[id];
+        for (int c = 0; c < n.nchild; ++c)
+            if (int rc = prepare_node(t, n.child[c], fields, nfields)) return rc;
+        auto ch = [&](int c) -> Node& { return t.nodes[n.child[c]]; };
+        switch (n.kind) {
+            case K_F: {
+                if (n.leaf >= nfields || !fields[n.leaf]) return fail(OPF_ERR_INVALID, "expression needs field argument %d", n.leaf);
+                const opf_field_s* f = fields[n.leaf];
+                for (int d = 0; d < D3; ++d) n.loc[d] = f->loc[d];
+                n.acc = f->accessible;
+                n.local = f->local;
+                n.logical = f->logical;
+                n.src = f;
+                break;
+            }
+            case K_S: n.scalar = true; break;
+            case K_COND: {
+                // CondOp::prepare (Conditional.hpp:45-70): props from arg2, ranges = common of the three
+                Node &c0 = ch(0), &c1 = ch(1), &c2 = ch(2);
+                if (c1.scalar || c2.scalar || c0.scalar) {
+                    // scalar operands carry no ranges
+                    const Node* firstf = !c1.scalar ? &c1 : (!c2.scalar ? &c2 : (!c0.scalar ? &c0 : nullptr));
+                    if (!firstf) {
+                        n.scalar = true;
+                        break;
+                    }
+                    inherit(n, *firstf);
+                    for (Node* o : {&c0, &c1, &c2})
+                        if (!o->scalar) {
+                            n.acc = common(n.acc, o->acc);
+                            n.local = common(n.local, o->local);
+                        }
+                    break;
+                }
+                for (int d = 0; d < D3; ++d)
+                    if (c0.loc[d] != c1.loc[d] || c0.loc[d] != c2.loc[d]) return fail(OPF_ERR_LOC, "conditional(): operands' loc differ");
+                inherit(n, c1);
+                n.acc = common(common(c0.acc, c1.acc), c2.acc);
+                n.local = common(common(c0.local, c1.local), c2.local);
+                break;
+            }
+            case K_D2C:// D2SecondOrderCentered::prepare (D2SecondOrderCentered.hpp:187-204)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.acc.start[n.axis]++, n.acc.end[n.axis]--;
+                n.logical.start[n.axis]++, n.logical.end[n.axis]--;
+                n.local.start[n.axis]++, n.local.end[n.axis]--;
+                break;
+            case K_D1C:// D1FirstOrderCentered::prepare (D1FirstOrderCentered.hpp:38-63)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                if (ch(0).loc[n.axis] == OPF_LOC_CENTER) {
+                    n.loc[n.axis] = OPF_LOC_CORNER;
+                    n.acc.start[n.axis]++, n.local.start[n.axis]++, n.logical.start[n.axis]++;
+                } else {
+                    n.loc[n.axis] = OPF_LOC_CENTER;
+                    n.acc.end[n.axis]--, n.local.end[n.axis]--, n.logical.end[n.axis]--;
+                }
+                break;
+            case K_D1DN:// D1FirstOrderBiasedDownwind::prepare (D1FirstOrderBiasedDownwind.hpp:68-84)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.acc.start[n.axis]++, n.logical.start[n.axis]++, n.local.start[n.axis]++;
+                break;
+            case K_D1UP:// D1FirstOrderBiasedUpwind::prepare (D1FirstOrderBiasedUpwind.hpp:68-84)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.acc.end[n.axis]--, n.logical.end[n.axis]--, n.local.end[n.axis]--;
+                break;
+            case K_WENODN:
+            case K_WENOUP:// D1WENO53*::prepare (D1WENO53Downwind.hpp:98-109): logicalRange is NOT shrunk
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.acc.start[n.axis] += 3, n.acc.end[n.axis] -= 3;
+                n.local.start[n.axis] += 3, n.local.end[n.axis] -= 3;
+                break;
+            case K_INTPC2N:// D1Linear<d,Cen2Cor>::prepare (D1Linear.hpp:50-59)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.loc[n.axis] = OPF_LOC_CORNER;
+                n.acc.start[n.axis]++, n.local.start[n.axis]++, n.logical.start[n.axis]++;
+                break;
+            case K_INTPN2C:// D1Linear<d,Cor2Cen>::prepare (D1Linear.hpp:60-69)
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
+                inherit(n, ch(0));
+                n.loc[n.axis] = OPF_LOC_CENTER;
+                n.acc.end[n.axis]--, n.logical.end[n.axis]--, n.local.end[n.axis]--;
+                break;
+            default:
+                if (n.nchild == 1) {// UniOp prepare (UniOpDefMacros.hpp.in:16-26)
+                    inherit(n, ch(0));
+                } else {// BinOp prepare (BinOpDefMacros.hpp.in:19-80)
+                    Node &a = ch(0), &b = ch(1);
+                    if (a.scalar && b.scalar) n.scalar = true;
+                    else if (a.scalar) inherit(n, b);
+                    else if (b.scalar) inherit(n, a);
+                    else {
+                        for (int d = 0; d < D3; ++d)
+                            if (a.loc[d] != b.loc[d]) return fail(OPF_ERR_LOC, "binary operator: operands' loc not same (axis %d)", d);
+                        inherit(n, a);// logicalRange stays arg1's
+                        n.acc = common(a.acc, b.acc);
+                        n.local = common(a.local, b.local);
+                    }
+                }
+        }
+        return OPF_OK;
+    }
+
+    // read footprint of every field leaf relative to the evaluation index (needs prepared loc)
+    static void footprint(const Tree& t, int id, const int lo_in[D3], const int hi_in[D3], int lo[][D3], int hi[][D3], bool* used,
+                          int mlo[D3], int mhi[D3]) {
+        const Node& n = t.nodes[id];
+        if (n.kind == K_F) {
+            for (int d = 0; d < D3; ++d) {
+                lo[n.leaf][d] = used[n.leaf] ? std::min(lo[n.leaf][d], lo_in[d]) : lo_in[d];
+                hi[n.leaf][d] = used[n.leaf] ? std::max(hi[n.leaf][d], hi_in[d]) : hi_in[d];
+            }
+            used[n.leaf] = true;
+            return;
+        }
+        int l[D3], h[D3];
+        for (int d = 0; d < D3; ++d) l[d] = lo_in[d], h[d] = hi_in[d];
+        if (n.axis >= 0) {
+            const int a = n.axis;
+            const bool center = t.nodes[n.child[0]].loc[a] == OPF_LOC_CENTER;
+            int ra = 0, rb = 0;// operand taps
+            int ma = 0, mb = 0;// mesh-array taps (dx / x indices)
+            switch (n.kind) {
+                case K_D2C: ra = -1, rb = 1, ma = -1, mb = center ? 1 : 0; break;
+                case K_D1C:
+                    if (center) ra = -1, rb = 0, ma = -1, mb = 0;
+                    else
+                        ra = 0, rb = 1, ma = 0, mb = 0;
+                    break;
+                case K_D1DN: ra = -1, rb = 0, ma = -1, mb = center ? 0 : -1; break;
+                case K_D1UP: ra = 0, rb = 1, ma = 0, mb = center ? 1 : 0; break;
+                case K_WENODN: ra = -3, rb = 2; break;
+                case K_WENOUP: ra = -2, rb = 3; break;
+                case K_INTPC2N: ra = -1, rb = 0, ma = -1, mb = 0; break;
+                case K_INTPN2C: ra = 0, rb = 1; break;
+            }
+            mlo[a] = std::min(mlo[a], lo_in[a] + ma - 1);// rdxh/rdxc reach one further
+            mhi[a] = std::max(mhi[a], hi_in[a] + mb + 1);
+            l[a] += ra;
+            h[a] += rb;
+        }
+        for (int c = 0; c < n.nchild; ++c) footprint(t, n.child[c], l, h, lo, hi, used, mlo, mhi);
+    }
+
+    // ------------------------------------------------------------------------------------------ registry
+    struct Registry {
+        std::mutex mu;
+        std::unordered_map<std::string, opf_expr_launcher> map;
+        std::vector<std::string> builtin;
+    };
+    static Registry& registry() {
+        static Registry r;
+        return r;
+    }
+    static std::string strip(const char* s) {
+        std::string o;
+        for (; *s; ++s)
+            if (*s != ' ') o.push_back(*s);
+        return o;
+    }
+    void register_builtin(const char* sig, opf_expr_launcher fn) {
+        Registry& r = registry();
+        std::lock_guard<std::mutex> g(r.mu);
+        std::string k = strip(sig);
+        if (!r.map.count(k)) r.builtin.push_back(k);
+        r.map[k] = fn;
+    }
+    static opf_expr_launcher find_launcher(const std::string& k) {
+        Registry& r = registry();
+        std::lock_guard<std::mutex> g(r.mu);
+        auto it = r.map.find(k);
+        return it == r.map.end() ? nullptr : it->second;
+    }
+
+    // ------------------------------------------------------------------------------------------ plan
+    struct Plan {
+        Tree tree;
+        opf_expr_launcher fn = nullptr;
+        std::string sig;
+    };
+    static std::unordered_map<std::string, std::unique_ptr<Plan>>& plan_cache() {
+        static std::unordered_map<std::string, std::unique_ptr<Plan>> c;
+        return c;
+    }
+    static int get_plan(const char* signature, Plan** out, bool need_launcher) {
+        std::string k = strip(signature);
+        auto& c = plan_cache();
+        auto it = c.find(k);
+        if (it == c.end()) {
+            auto p = std::make_unique<Plan>();
+            p->sig = k;
+            if (int rc = parse_signature(k.c_str(), p->tree)) return rc;
+            it = c.emplace(k, std::move(p)).first;
+        }
+        Plan* p = it->second.get();
+        if (need_launcher && !p->fn) {
+            p->fn = find_launcher(k);
+            if (!p->fn)
+                return fail(OPF_ERR_UNSUPPORTED,
+                            "expression '%s' has no compiled device kernel: compile the program with nvcc against <OpFlow> "
+                            "(registers it) or add it to opflow_b200/csrc/builtin_exprs.cu",
+                            k.c_str());
+        }
+        *out = p;
+        return OPF_OK;
+    }
+
+    static int fill_args(Plan& p, const opf_field_t* fields, int nfields, const double* scalars, int nscalars, const Range& r,
+                         const opf_mesh_s* mesh_hint, opf::ExprArgs& a, int& alias0) {
+        Tree& t = p.tree;
+        if (nfields < t.nfields) return fail(OPF_ERR_INVALID, "expression '%s' needs %d fields, got %d", p.sig.c_str(), t.nfields, nfields);
+        if (nscalars < t.nscalars) return fail(OPF_ERR_INVALID, "expression '%s' needs %d scalars, got %d", p.sig.c_str(), t.nscalars, nscalars);
+        if (int rc = prepare_node(t, 0, fields, nfields)) return rc;
+        memset(&a, 0, sizeof a);
+        const opf_mesh_s* mesh = mesh_hint;
+        alias0 = t.nfields > 1;
+        for (int k = 0; k < t.nfields; ++k) {
+            const opf_field_s* f = fields[k];
+            if (!f) return fail(OPF_ERR_INVALID, "field argument %d is null", k);
+            a.f[k].p = f->biased(f->cur);
+            a.f[k].s1 = f->pitch1;
+            a.f[k].s2 = f->pitch2;
+            if (f != fields[0]) alias0 = 0;
+            if (!mesh) mesh = f->mesh;
+            // operands must live on the same mesh (BinOpDefMacros.hpp.in:21-22 asserts mesh equality)
+            if (mesh != f->mesh) {
+                for (int d = 0; d < mesh->dim; ++d)
+                    if (mesh->ax[d].x != f->mesh->ax[d].x || mesh->ext_range.start[d] != f->mesh->ext_range.start[d])
+                        return fail(OPF_ERR_INVALID, "operands of '%s' live on different meshes", p.sig.c_str());
+            }
+        }
+        for (int k = 0; k < t.nscalars; ++k) a.s[k] = scalars[k];
+        if (mesh)
+            for (int d = 0; d < mesh->dim; ++d) a.ax[d] = mesh_axis_view(mesh, d);
+        for (size_t i = 0; i < t.nodes.size(); ++i) {
+            const Node& n = t.nodes[i];
+            unsigned char bits = 0;
+            if (n.axis >= 0) {
+                const Node& c = t.nodes[n.child[0]];
+                for (int d = 0; d < D3; ++d)
+                    if (c.loc[d] == OPF_LOC_CENTER) bits |= 1u << d;
+            }
+            a.loc[i] = bits;
+        }
+        // bounds: every tap of every leaf over the evaluation box must lie inside that leaf's storage
+        if (r.count() > 0 && t.nfields > 0) {
+            int lo[OPF_MAX_FIELDS][D3], hi[OPF_MAX_FIELDS][D3];
+            bool used[OPF_MAX_FIELDS] = {false};
+            int z[D3] = {0, 0, 0};
+            int mlo[D3] = {0, 0, 0}, mhi[D3] = {0, 0, 0};
+            footprint(t, 0, z, z, lo, hi, used, mlo, mhi);
+            for (int k = 0; k < t.nfields; ++k) {
+                if (!used[k]) continue;
+                const opf_field_s* f = fields[k];
+                for (int d = 0; d < f->dim; ++d)
+                    if (r.start[d] + lo[k][d] < f->storage.start[d] || r.end[d] + hi[k][d] > f->storage.end[d])
+                        return fail(OPF_ERR_RANGE,
+                                    "expression '%s' evaluated over [%d,%d) on axis %d reads field '%s' at offsets [%d,%d] outside its storage "
+                                    "[%d,%d): increase setExt/setPadding",
+                                    p.sig.c_str(), r.start[d], r.end[d], d, f->name.c_str(), lo[k][d], hi[k][d], f->storage.start[d],
+                                    f->storage.end[d]);
+            }
+            if (mesh)
+                for (int d = 0; d < mesh->dim; ++d)
+                    if (r.start[d] + mlo[d] < mesh->ext_range.start[d] || r.end[d] - 1 + mhi[d] >= mesh->ext_range.end[d])
+                        return fail(OPF_ERR_RANGE, "expression '%s' reads mesh spacings outside the mesh's extended range on axis %d", p.sig.c_str(), d);
+        }
+        return OPF_OK;
+    }
+}// namespace opfe
+
+using namespace opfe;
+
+extern "C" {
+
+int opf_expr_register(const char* signature, opf_expr_launcher fn) {
+    if (!signature || !fn) return fail(OPF_ERR_INVALID, "null argument");
+    Registry& r = registry();
+    std::lock_guard<std::mutex> g(r.mu);
+    r.map[strip(signature)] = fn;
+    return OPF_OK;
+}
+int opf_expr_is_registered(const char* signature) { return signature && find_launcher(strip(signature)) != nullptr; }
+int opf_expr_builtin_count(void) { return (int) registry().builtin.size(); }
+const char* opf_expr_builtin_name(int i) {
+    auto& b = registry().builtin;
+    return i >= 0 && i < (int) b.size() ? b[i].c_str() : nullptr;
+}
+
+int opf_expr_prepare(const char* signature, const opf_field_t* fields, int nfields, int which, opf_range* out, int* loc) {
+    Plan* p;
+    if (int rc = get_plan(signature, &p, false)) return rc;
+    if (nfields < p->tree.nfields) return fail(OPF_ERR_INVALID, "need %d fields", p->tree.nfields);
+    if (int rc = prepare_node(p->tree, 0, fields, nfields)) return rc;
+    const Node& n = p->tree.nodes[0];
+    if (out) {
+        switch (which) {
+            case 0: *out = to_c(n.local); break;
+            case 2: *out = to_c(n.acc); break;
+            case 3: *out = to_c(n.logical); break;
+            case 1: {
+                Range e;
+                e.set_empty(n.src ? n.src->dim : D3);
+                *out = to_c(e);
+                break;
+            }
+            default: return fail(OPF_ERR_INVALID, "bad selector");
+        }
+    }
+    if (loc)
+        for (int d = 0; d < D3; ++d) loc[d] = n.loc[d];
+    return OPF_OK;
+}
+
+int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
+               int nscalars) {
+    if (!dst || !signature) return fail(OPF_ERR_INVALID, "null argument");
+    if (op < 0 || op > 4) return fail(OPF_ERR_UNSUPPORTED, "assign op %d is integer-only in the reference (Mod/And/Or/Xor/Shift)", op);
+    if (int rc = require_device()) return rc;
+    Plan* p;
+    if (int rc = get_plan(signature, &p, true)) return rc;
+    const Range w = common(dst->assignable, dst->local);// FieldAssigner.hpp:49
+    opf::ExprArgs a;
+    int alias0 = 0;
+    if (int rc = fill_args(*p, fields, nfields, scalars, nscalars, w, dst->mesh, a, alias0)) return rc;
+    // src.contains(dst) (FieldAssigner.hpp:28, CartesianField.hpp:793)
+    bool alias = false;
+    for (int k = 0; k < p->tree.nfields; ++k)
+        if (fields[k] == dst) alias = true;
+    // a pure point-wise expression of dst itself may be updated in place (no neighbour taps)
+    bool has_stencil = false;
+    for (const auto& n : p->tree.nodes)
+        if (n.axis >= 0) has_stencil = true;
+    const bool use_twin = alias && has_stencil;
+    if (use_twin)
+        if (int rc = field_ensure_twin(dst)) return rc;
+    opf::LaunchInfo li;
+    memset(&li, 0, sizeof li);
+    const int wr = use_twin ? 1 - dst->cur : dst->cur;
+    li.dst.p = dst->biased(wr);
+    li.dst.s1 = dst->pitch1;
+    li.dst.s2 = dst->pitch2;
+    li.old = dst->biased(dst->cur);
+    for (int d = 0; d < 3; ++d) {
+        li.r.lo[d] = w.start[d];
+        li.r.hi[d] = w.end[d];
+    }
+    li.dim = dst->dim;
+    li.op = op;
+    li.mode = ctx().mode;
+    li.alias0 = alias0;
+    li.rop = -1;
+    if (w.count() > 0) {
+        const int rc = p->fn(&a, &li, ctx().stream);
+        if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have");
+        ctx().launches++;
+    }
+    if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep
+    return field_update_padding(dst);// CartesianField.hpp:231
+}
+
+int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src) {
+    if (!dst || !src) return fail(OPF_ERR_INVALID, "null field");
+    if (dst == src && op == OPF_OP_EQ) return OPF_OK;// CartesianField.hpp:188 (this != &other)
+    const opf_field_t fs[1] = {src};
+    return opf_assign(dst, op, "F<0>", fs, 1, nullptr, 0);
+}
+
+int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
+               const opf_range* range, double* result) {
+    if (!signature || !result) return fail(OPF_ERR_INVALID, "null argument");
+    if (rop < 0 || rop > 4) return fail(OPF_ERR_INVALID, "bad reduce op");
+    if (int rc = require_device()) return rc;
+    Plan* p;
+    if (int rc = get_plan(signature, &p, true)) return rc;
+    if (nfields < 1) return fail(OPF_ERR_INVALID, "reduce needs at least one field");
+    // range must be known before the bounds check: prepare first to get the expression's own ranges
+    if (int rc = prepare_node(p->tree, 0, fields, nfields)) return rc;
+    const Node& root = p->tree.nodes[0];
+    Range r = range ? from_c(*range, fields[0]->dim) : common(root.local, root.acc);
+    opf::ExprArgs a;
+    int alias0 = 0;
+    if (int rc = fill_args(*p, fields, nfields, scalars, nscalars, r, fields[0]->mesh, a, alias0)) return rc;
+    Context& c = ctx();
+    if (r.count() <= 0) {
+        *result = rop == OPF_RED_MAX ? -INFINITY : (rop == OPF_RED_MIN ? INFINITY : 0.0);
+        return OPF_OK;
+    }
+    opf::LaunchInfo li;
+    memset(&li, 0, sizeof li);
+    for (int d = 0; d < 3; ++d) {
+        li.r.lo[d] = r.start[d];
+        li.r.hi[d] = r.end[d];
+    }
+    li.dim = fields[0]->dim;
+    li.mode = c.mode;
+    li.alias0 = alias0;
+    li.rop = rop;
+    const long long rows = (long long) (r.end[1] - r.start[1]) * (r.end[2] - r.start[2]);
+    const long long items = rows * ((r.end[0] - r.start[0] + opf::RED_SEG - 1) / opf::RED_SEG);
+    li.n_partials = (int) std::max<long long>(1, std::min<long long>(items, 4LL * c.sm_count));
+    li.partials = c.red_buf;
+    const int rc = p->fn(&a, &li, c.stream);
+    if (rc != 0) return fail(OPF_ERR_CUDA, "reduce launch of '%s' failed", p->sig.c_str());
+    c.launches += 2;
+    OPF_CUDA(cudaMemcpyAsync(c.red_host, c.red_buf + li.n_partials, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    OPF_CUDA(cudaStreamSynchronize(c.stream));
+    *result = c.red_host[0];
+    return OPF_OK;
+}
+
+}// extern "C"
