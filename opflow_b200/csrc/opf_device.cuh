@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdlib>
 
 namespace opf {
 
@@ -277,10 +278,11 @@ namespace opf {
             const double s3 = 13. / 12. * t5 * t5 + t6 * t6 * 0.25;
             const double eps = 1e-6 * fmax(fmax(fmax(d1 * d1, d2 * d2), fmax(d3 * d3, d4 * d4)), d5 * d5) + 1e-99;
             const double e1 = s1 + eps, e2 = s2 + eps, e3 = s3 + eps;
-            // a_k = g_k / e_k^2 ; w_k = a_k / sum  ==  g_k * (e_m e_n)^2 / sum_k g_k (e_m e_n)^2  (one divide)
-            const double p23 = e2 * e3, p13 = e1 * e3, p12 = e1 * e2;
-            const double n1 = .1 * p23 * p23, n2 = .6 * p13 * p13, n3 = .3 * p12 * p12;
-            return (n1 * ddx1 + n2 * ddx2 + n3 * ddx3) / (n1 + n2 + n3);
+            // a_k = g_k / e_k^2 (e_k can be ~1e-99 on flat data: keep the reference's form, no cross-products that
+            // would underflow); one reciprocal of the sum instead of three divides
+            const double a1 = .1 / (e1 * e1), a2 = .6 / (e2 * e2), a3 = .3 / (e3 * e3);
+            const double inv = 1. / (a1 + a2 + a3);
+            return (a1 * ddx1 + a2 * ddx2 + a3 * ddx3) * inv;
         } else {
             const double ddx1 = P::add(P::sub(P::div(d1, 3.), P::div(P::mul(7., d2), 6.)), P::div(P::mul(11., d3), 6.));
             const double ddx2 = P::add(P::add(P::div(-d2, 6.), P::div(P::mul(5., d3), 6.)), P::div(d4, 3.));
@@ -529,10 +531,14 @@ namespace opf {
             g.ch = 16;
             g.grid = dim3((n0 + tx - 1) / tx, (n1 + g.ch - 1) / g.ch, 1);
         } else {
-            const int tx = pick_tx(n0);
-            const int ty = 4;
+            // tunables for sweeps (read once): OPF_TX / OPF_TY / OPF_CH
+            static const int etx = getenv("OPF_TX") ? atoi(getenv("OPF_TX")) : 0;
+            static const int ety = getenv("OPF_TY") ? atoi(getenv("OPF_TY")) : 0;
+            static const int ech = getenv("OPF_CH") ? atoi(getenv("OPF_CH")) : 0;
+            const int tx = etx > 0 ? etx : pick_tx(n0);
+            const int ty = ety > 0 ? ety : 4;
             g.block = dim3(tx, ty, 1);
-            g.ch = 32;
+            g.ch = ech > 0 ? ech : 32;
             g.grid = dim3((n0 + tx - 1) / tx, (n1 + ty - 1) / ty, (n2 + g.ch - 1) / g.ch);
         }
         return g;

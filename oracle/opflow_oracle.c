@@ -217,7 +217,7 @@ static void fill_cell(const int* g, void* ud) {
         f->data[f_off(f, g)] = c->bc;
         return;
     }
-    if (c->kind == 5) {/* periodic copy :609-629 */
+    if (c->kind == 100) {/* periodic copy :609-629 */
         mir[i] += c->side == 0 ? (f->accessible.end[i] - f->accessible.start[i]) : -(f->accessible.end[i] - f->accessible.start[i]);
         f->data[f_off(f, g)] = f_get(f, mir);
         return;
@@ -300,7 +300,7 @@ void orc_update_padding(orc_field* f, const orc_mesh* m) {
         if (f->bc_type[i][0] == BC_PERIODIC) {
             orc_range r = f->logical;
             r.end[i] = f->accessible.start[i];
-            c.axis = i, c.side = 0, c.kind = 5;
+            c.axis = i, c.side = 0, c.kind = 100;
             for_box(&r, &f->storage, fill_cell, &c);
             r = f->logical;
             r.start[i] = f->accessible.end[i];
