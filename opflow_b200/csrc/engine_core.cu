@@ -278,21 +278,22 @@ int opf_mesh_destroy(opf_mesh_t m) {
 }// extern "C"
 
 namespace opfe {
+    constexpr int MESH_SLACK = 32;// speculative coefficient loads of the window skeleton stay in bounds
     int mesh_upload(opf_mesh_s* m) {
         if (m->device_ready) return OPF_OK;
         for (int d = 0; d < m->dim; ++d) {
             auto& a = m->ax[d];
             if (!a.set) return fail(OPF_ERR_INVALID, "mesh axis %d has no coordinates (setMeshOfDim missing)", d);
-            const size_t n = a.x.size();
+            const size_t n = a.x.size(), st = n + 2 * MESH_SLACK;// each array: SLACK zeros | n values | SLACK zeros
             if (a.dev) cudaFree(a.dev);
-            OPF_CUDA(cudaMalloc(&a.dev, sizeof(double) * n * 5));
-            std::vector<double> h(n * 5, 0.0);
-            std::copy(a.x.begin(), a.x.end(), h.begin());
-            std::copy(a.dx.begin(), a.dx.end(), h.begin() + n);
-            std::copy(a.rdx.begin(), a.rdx.end(), h.begin() + 2 * n);
-            std::copy(a.rdxh.begin(), a.rdxh.end(), h.begin() + 3 * n);
-            std::copy(a.rdxc.begin(), a.rdxc.end(), h.begin() + 4 * n);
-            OPF_CUDA(cudaMemcpy(a.dev, h.data(), sizeof(double) * n * 5, cudaMemcpyHostToDevice));
+            OPF_CUDA(cudaMalloc(&a.dev, sizeof(double) * st * 5));
+            std::vector<double> h(st * 5, 0.0);
+            std::copy(a.x.begin(), a.x.end(), h.begin() + MESH_SLACK);
+            std::copy(a.dx.begin(), a.dx.end(), h.begin() + st + MESH_SLACK);
+            std::copy(a.rdx.begin(), a.rdx.end(), h.begin() + 2 * st + MESH_SLACK);
+            std::copy(a.rdxh.begin(), a.rdxh.end(), h.begin() + 3 * st + MESH_SLACK);
+            std::copy(a.rdxc.begin(), a.rdxc.end(), h.begin() + 4 * st + MESH_SLACK);
+            OPF_CUDA(cudaMemcpy(a.dev, h.data(), sizeof(double) * st * 5, cudaMemcpyHostToDevice));
         }
         m->device_ready = true;
         return OPF_OK;
@@ -300,13 +301,13 @@ namespace opfe {
     opf::AxisView mesh_axis_view(const opf_mesh_s* m, int d) {
         opf::AxisView v{nullptr, nullptr, nullptr, nullptr, nullptr};
         if (d >= m->dim || !m->ax[d].dev) return v;
-        const long long n = (long long) m->ax[d].x.size();
-        const double* base = m->ax[d].dev - m->ext_range.start[d];
+        const long long st = (long long) m->ax[d].x.size() + 2 * MESH_SLACK;
+        const double* base = m->ax[d].dev + MESH_SLACK - m->ext_range.start[d];
         v.x = base;
-        v.dx = base + n;
-        v.rdx = base + 2 * n;
-        v.rdxh = base + 3 * n;
-        v.rdxc = base + 4 * n;
+        v.dx = base + st;
+        v.rdx = base + 2 * st;
+        v.rdxh = base + 3 * st;
+        v.rdxc = base + 4 * st;
         return v;
     }
 }// namespace opfe

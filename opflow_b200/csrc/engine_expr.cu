@@ -6,6 +6,8 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <cstdint>
+#include <cstdlib>
 
 namespace opfe {
 
@@ -438,6 +440,48 @@ namespace opfe {
 
 using namespace opfe;
 
+// CUtensorMap factory for the TMA tile skeleton (called by the launcher templates, also from user translation units).
+// Descriptors are cached by (base, dims, strides, box): the ping-pong buffers of a field alternate between two entries.
+extern "C" int opf_internal_tensor_map(void* out128, const void* base, const unsigned long long* dims, const unsigned long long* strides_b,
+                                       const unsigned* box, int rank) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static std::map<std::string, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 1;
+        encode = (encode_fn) fn;
+    }
+    std::string key((const char*) &base, sizeof base);
+    key.append((const char*) dims, sizeof(unsigned long long) * rank);
+    key.append((const char*) strides_b, sizeof(unsigned long long) * (rank - 1));
+    key.append((const char*) box, sizeof(unsigned) * rank);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        CUtensorMap m;
+        cuuint64_t gd[5], gs[5];
+        cuuint32_t bx[5], es[5];
+        for (int i = 0; i < rank; ++i) {
+            gd[i] = dims[i];
+            bx[i] = box[i];
+            es[i] = 1;
+        }
+        for (int i = 0; i < rank - 1; ++i) gs[i] = strides_b[i];
+        CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t) rank, const_cast<void*>(base), gd, gs, bx, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return 2;
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(key, m).first;
+    }
+    memcpy(out128, &it->second, sizeof(CUtensorMap));
+    return 0;
+}
+
 extern "C" {
 
 int opf_expr_register(const char* signature, opf_expr_launcher fn) {
@@ -517,6 +561,31 @@ int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t
     li.mode = ctx().mode;
     li.alias0 = alias0;
     li.rop = -1;
+    // register-window skeleton: vector loads need 16-byte aligned rows at the first evaluated cell
+    static const int window_on = getenv("OPF_WINDOW") ? atoi(getenv("OPF_WINDOW")) : 1;
+    li.window = window_on && dst->dim >= 2 && (w.end[0] - w.start[0]) >= 8;
+    li.valign = 0;
+    for (int k = 0; k < p->tree.nfields; ++k) {
+        const opf_field_s* f = fields[k];
+        const bool al = ((reinterpret_cast<uintptr_t>(f->biased(f->cur) + w.start[0]) & 15) == 0) && (f->pitch1 % 2 == 0) && (f->pitch2 % 2 == 0);
+        if (al) li.valign |= 1u << k;
+    }
+    li.dalign = ((reinterpret_cast<uintptr_t>(li.dst.p + w.start[0]) & 15) == 0) && (dst->pitch1 % 2 == 0) && (dst->pitch2 % 2 == 0);
+    li.tma_ok = dst->dim == 3;
+    for (int k = 0; k < p->tree.nfields && li.tma_ok; ++k) {
+        const opf_field_s* f = fields[alias0 ? 0 : k];
+        auto& t = li.tma[k];
+        t.base = f->buf[f->cur];
+        t.dim[0] = (unsigned long long) f->pitch1;
+        t.dim[1] = (unsigned long long) (f->storage.end[1] - f->storage.start[1]);
+        t.dim[2] = (unsigned long long) (f->storage.end[2] - f->storage.start[2]);
+        t.stride_b[0] = (unsigned long long) f->pitch1 * 8ull;
+        t.stride_b[1] = (unsigned long long) f->pitch2 * 8ull;
+        t.org[0] = f->storage.start[0] - (int) f->lead;
+        t.org[1] = f->storage.start[1];
+        t.org[2] = f->storage.start[2];
+        if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.stride_b[0] & 15) || (t.stride_b[1] & 15) || f->dim != 3) li.tma_ok = 0;
+    }
     if (w.count() > 0) {
         const int rc = p->fn(&a, &li, ctx().stream);
         if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have");

@@ -12,6 +12,7 @@
 //            (<= 1e-12 relative vs the reference).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cstdlib>
@@ -58,6 +59,16 @@ namespace opf {
         int op;   // opf_assign_op
         int mode; // opf_mode
         int alias0;// all field leaves are the same field -> read everything through f[0]
+        unsigned valign;// bit s: rows of field slot s are 16-byte aligned at r.lo[0] (vector loads allowed)
+        int dalign;     // same for dst
+        int window;     // 0: direct-global skeleton, >0: register-window skeleton allowed
+        // TMA tile skeleton (3-D): per field slot the tensor behind the pitched storage; tensor coord = global index - org
+        struct TmaSlot {
+            const void* base;
+            unsigned long long dim[3], stride_b[2];
+            int org[3];
+        } tma[MAX_FIELDS];
+        int tma_ok;// every slot is TMA-addressable (16-byte aligned base and strides)
         // reduction launches
         int rop;
         double* partials;// >= grid blocks
@@ -84,9 +95,59 @@ namespace opf {
     __device__ __forceinline__ int axis_of(int i, int j, int k) {
         return D == 0 ? i : (D == 1 ? j : k);
     }
+#ifndef OPF_WIN_MINBLOCKS
+#define OPF_WIN_MINBLOCKS 6
+#endif
 #define OPF_SHIFT(D, n) i + ((D) == 0 ? (n) : 0), j + ((D) == 1 ? (n) : 0), k + ((D) == 2 ? (n) : 0)
 
+    // ------------------------------------------------------------------------------------------- tap sets
+    // Compile-time footprint of an expression: for every field slot the set of relative offsets (di,dj,dk) it is read
+    // at.  The register-window skeleton sizes its per-thread windows from it.  Radius is capped at WR per axis; larger
+    // footprints (overflow) use the direct-global skeleton.
+    constexpr int WR = 3, WN = 2 * WR + 1;
+    struct TapGrid {
+        bool t[WN][WN][WN] = {};// [dk+WR][dj+WR][di+WR]
+        bool overflow = false;
+    };
+    constexpr TapGrid tap_origin() {
+        TapGrid g;
+        g.t[WR][WR][WR] = true;
+        return g;
+    }
+    // Minkowski sum of a tap grid with offsets [lo,hi] along axis D
+    constexpr TapGrid tap_shift(const TapGrid& in, int D, int lo, int hi) {
+        TapGrid o;
+        o.overflow = in.overflow;
+        for (int k = 0; k < WN; ++k)
+            for (int j = 0; j < WN; ++j)
+                for (int i = 0; i < WN; ++i)
+                    if (in.t[k][j][i])
+                        for (int d = lo; d <= hi; ++d) {
+                            const int ii = i + (D == 0 ? d : 0), jj = j + (D == 1 ? d : 0), kk = k + (D == 2 ? d : 0);
+                            if (ii < 0 || ii >= WN || jj < 0 || jj >= WN || kk < 0 || kk >= WN) o.overflow = true;
+                            else
+                                o.t[kk][jj][ii] = true;
+                        }
+        return o;
+    }
+    template <int NS>
+    struct TapSet {
+        TapGrid g[NS > 0 ? NS : 1];
+        bool overflow = false;
+        constexpr void add(int slot, const TapGrid& in) {
+            for (int k = 0; k < WN; ++k)
+                for (int j = 0; j < WN; ++j)
+                    for (int i = 0; i < WN; ++i)
+                        if (in.t[k][j][i]) g[slot].t[k][j][i] = true;
+            if (in.overflow) overflow = true;
+        }
+    };
+
     // ------------------------------------------------------------------------------------------- leaves
+    // Every node offers two evaluators with identical arithmetic:
+    //   eval<B,P,A0>(args, i,j,k)            run-time coordinates, loads straight from global memory
+    //   ev<B,P,A0,DI,DJ,DK>(ctx)             compile-time offsets relative to the thread's tile origin; leaves read the
+    //                                        thread's register window (ctx.get<slot,DI,DJ,DK>())
     // CartesianField::evalAtImpl_final (CartesianField.hpp:775-780)
     template <int K>
     struct F {
@@ -95,6 +156,14 @@ namespace opf {
         __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
             const FieldView& v = a.f[A0 ? 0 : K];
             return __ldg(v.p + ((long long) i + (long long) j * v.s1 + (long long) k * v.s2));
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            return c.template get<(A0 ? 0 : K), DI, DJ, DK>();
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            ts.add(A0 ? 0 : K, in);
         }
     };
     // ScalarExpr<T>::evalAt ignores the index (ScalarExpr.hpp:36)
@@ -105,6 +174,12 @@ namespace opf {
         __device__ __forceinline__ static double eval(const ExprArgs& a, int, int, int) {
             return a.s[K];
         }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            return c.a.s[K];
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS&, const TapGrid&) {}
     };
 
     // ------------------------------------------------------------------------------------------- point-wise
@@ -115,11 +190,26 @@ namespace opf {
         static constexpr int size = 1 + L::size + R::size;                                                             \
         static constexpr int maxaxis = L::maxaxis > R::maxaxis ? L::maxaxis : R::maxaxis;                              \
         static constexpr int nf = L::nf > R::nf ? L::nf : R::nf;                                                       \
+        template <class P>                                                                                             \
+        __device__ __forceinline__ static double math(double x, double y) {                                            \
+            return EXPR;                                                                                               \
+        }                                                                                                              \
         template <int B, class P, bool A0>                                                                             \
         __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {                        \
             const double x = L::template eval<B + 1, P, A0>(a, i, j, k);                                               \
             const double y = R::template eval<B + 1 + L::size, P, A0>(a, i, j, k);                                     \
-            return EXPR;                                                                                               \
+            return math<P>(x, y);                                                                                      \
+        }                                                                                                              \
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>                                            \
+        __device__ __forceinline__ static double ev(const C& c) {                                                      \
+            const double x = L::template ev<B + 1, P, A0, DI, DJ, DK>(c);                                              \
+            const double y = R::template ev<B + 1 + L::size, P, A0, DI, DJ, DK>(c);                                    \
+            return math<P>(x, y);                                                                                      \
+        }                                                                                                              \
+        template <bool A0, class TS>                                                                                   \
+        static constexpr void taps(TS& ts, const TapGrid& in) {                                                        \
+            L::template taps<A0>(ts, in);                                                                              \
+            R::template taps<A0>(ts, in);                                                                              \
         }                                                                                                              \
     };
     OPF_BINOP(Add, P::add(x, y))
@@ -143,10 +233,21 @@ namespace opf {
     template <class E>                                                                                                 \
     struct Name {                                                                                                      \
         static constexpr int size = 1 + E::size, maxaxis = E::maxaxis, nf = E::nf;                                     \
+        template <class P>                                                                                             \
+        __device__ __forceinline__ static double math(double x) {                                                      \
+            return EXPR;                                                                                               \
+        }                                                                                                              \
         template <int B, class P, bool A0>                                                                             \
         __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {                        \
-            const double x = E::template eval<B + 1, P, A0>(a, i, j, k);                                               \
-            return EXPR;                                                                                               \
+            return math<P>(E::template eval<B + 1, P, A0>(a, i, j, k));                                                \
+        }                                                                                                              \
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>                                            \
+        __device__ __forceinline__ static double ev(const C& c) {                                                      \
+            return math<P>(E::template ev<B + 1, P, A0, DI, DJ, DK>(c));                                               \
+        }                                                                                                              \
+        template <bool A0, class TS>                                                                                   \
+        static constexpr void taps(TS& ts, const TapGrid& in) {                                                        \
+            E::template taps<A0>(ts, in);                                                                              \
         }                                                                                                              \
     };
     OPF_UNIOP(Neg, -x)
@@ -164,100 +265,148 @@ namespace opf {
 #undef OPF_UNIOP
 
     // CondOp::eval (Conditional.hpp:37-40)
-    template <class C, class A, class Bb>
+    template <class Cc, class A, class Bb>
     struct Cond {
-        static constexpr int size = 1 + C::size + A::size + Bb::size;
-        static constexpr int maxaxis = (C::maxaxis > A::maxaxis ? C::maxaxis : A::maxaxis) > Bb::maxaxis
-                                               ? (C::maxaxis > A::maxaxis ? C::maxaxis : A::maxaxis)
+        static constexpr int size = 1 + Cc::size + A::size + Bb::size;
+        static constexpr int maxaxis = (Cc::maxaxis > A::maxaxis ? Cc::maxaxis : A::maxaxis) > Bb::maxaxis
+                                               ? (Cc::maxaxis > A::maxaxis ? Cc::maxaxis : A::maxaxis)
                                                : Bb::maxaxis;
-        static constexpr int nf = (C::nf > A::nf ? C::nf : A::nf) > Bb::nf ? (C::nf > A::nf ? C::nf : A::nf) : Bb::nf;
+        static constexpr int nf = (Cc::nf > A::nf ? Cc::nf : A::nf) > Bb::nf ? (Cc::nf > A::nf ? Cc::nf : A::nf) : Bb::nf;
         template <int B, class P, bool A0>
         __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const double c = C::template eval<B + 1, P, A0>(a, i, j, k);
-            return c != 0.0 ? A::template eval<B + 1 + C::size, P, A0>(a, i, j, k)
-                            : Bb::template eval<B + 1 + C::size + A::size, P, A0>(a, i, j, k);
+            const double c = Cc::template eval<B + 1, P, A0>(a, i, j, k);
+            return c != 0.0 ? A::template eval<B + 1 + Cc::size, P, A0>(a, i, j, k)
+                            : Bb::template eval<B + 1 + Cc::size + A::size, P, A0>(a, i, j, k);
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            const double cv = Cc::template ev<B + 1, P, A0, DI, DJ, DK>(c);
+            return cv != 0.0 ? A::template ev<B + 1 + Cc::size, P, A0, DI, DJ, DK>(c)
+                             : Bb::template ev<B + 1 + Cc::size + A::size, P, A0, DI, DJ, DK>(c);
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            Cc::template taps<A0>(ts, in);
+            A::template taps<A0>(ts, in);
+            Bb::template taps<A0>(ts, in);
         }
     };
 
     // ------------------------------------------------------------------------------------------- stencils
+    // helper: boilerplate shared by all 1-operand stencil nodes.  TAP(n) evaluates the operand at offset n along axis D.
+#define OPF_STENCIL_HEAD(LO, HI)                                                                                       \
+    static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;                  \
+    template <bool A0, class TS>                                                                                       \
+    static constexpr void taps(TS& ts, const TapGrid& in) {                                                            \
+        E::template taps<A0>(ts, tap_shift(in, D, LO, HI));                                                            \
+    }
+#define OPF_EVAL_BEGIN                                                                                                 \
+    template <int B, class P, bool A0>                                                                                 \
+    __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {                            \
+        const GAcc acc{a.ax[D], axis_of<D>(i, j, k)};                                                                  \
+        auto TAP = [&](auto n) { return E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, decltype(n)::value)); };
+#define OPF_EV_BEGIN                                                                                                   \
+    template <int B, class P, bool A0, int DI, int DJ, int DK, class C>                                                \
+    __device__ __forceinline__ static double ev(const C& c) {                                                          \
+        const ExprArgs& a = c.a;                                                                                       \
+        const WAcc<C, D, (D == 0 ? DI : (D == 1 ? DJ : DK))> acc{c};                                                   \
+        auto TAP = [&](auto n) {                                                                                       \
+            constexpr int o = decltype(n)::value;                                                                      \
+            return E::template ev<B + 1, P, A0, DI + (D == 0 ? o : 0), DJ + (D == 1 ? o : 0), DK + (D == 2 ? o : 0)>(c); \
+        };
+    template <int N>
+    struct IC {
+        static constexpr int value = N;
+    };
+    // mesh-coefficient accessors: O is the compile-time offset from the stencil's own index q along its axis
+    enum { CF_X = 0, CF_DX = 1, CF_RDX = 2, CF_RDXH = 3, CF_RDXC = 4 };
+    struct GAcc {// direct global loads (run-time coordinate evaluator)
+        const AxisView& ax;
+        int q;
+        template <int O> __device__ __forceinline__ double x() const { return __ldg(ax.x + q + O); }
+        template <int O> __device__ __forceinline__ double dx() const { return __ldg(ax.dx + q + O); }
+        template <int O> __device__ __forceinline__ double rdx() const { return __ldg(ax.rdx + q + O); }
+        template <int O> __device__ __forceinline__ double rdxh() const { return __ldg(ax.rdxh + q + O); }
+        template <int O> __device__ __forceinline__ double rdxc() const { return __ldg(ax.rdxc + q + O); }
+    };
+    template <class C, int D, int QO>
+    struct WAcc {// register-cached coefficients of the window context (hoisted out of the march loop)
+        const C& c;
+        template <int O> __device__ __forceinline__ double x() const { return c.template coef<D, CF_X, QO + O>(); }
+        template <int O> __device__ __forceinline__ double dx() const { return c.template coef<D, CF_DX, QO + O>(); }
+        template <int O> __device__ __forceinline__ double rdx() const { return c.template coef<D, CF_RDX, QO + O>(); }
+        template <int O> __device__ __forceinline__ double rdxh() const { return c.template coef<D, CF_RDXH, QO + O>(); }
+        template <int O> __device__ __forceinline__ double rdxc() const { return c.template coef<D, CF_RDXC, QO + O>(); }
+    };
+
     // D2SecondOrderCentered<d>::eval (D2SecondOrderCentered.hpp:161-171)
+    template <class P, class Acc>
+    __device__ __forceinline__ double d2c_math(double l, double c, double r, bool center, const Acc& m) {
+        if constexpr (P::fast) {
+            if (!center) return ((r - c) * m.template rdx<0>() - (c - l) * m.template rdx<-1>()) * m.template rdxh<0>();
+            return ((r - c) * m.template rdxh<1>() - (c - l) * m.template rdxh<0>()) * m.template rdxc<0>();
+        } else {
+            double dxl, dxr;
+            if (!center) {
+                dxl = m.template dx<-1>();
+                dxr = m.template dx<0>();
+            } else {
+                dxl = P::mul(P::add(m.template dx<-1>(), m.template dx<0>()), 0.5);
+                dxr = P::mul(P::add(m.template dx<0>(), m.template dx<1>()), 0.5);
+            }
+            const double dxc = P::mul(P::add(dxl, dxr), 0.5);
+            return P::div(P::sub(P::div(P::sub(r, c), dxr), P::div(P::sub(c, l), dxl)), dxc);
+        }
+    }
     template <int D, class E>
     struct D2C {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const double l = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-            const double c = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double r = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-            const bool center = (a.loc[B] >> D) & 1;
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            if constexpr (P::fast) {
-                if (!center) return ((r - c) * __ldg(ax.rdx + q) - (c - l) * __ldg(ax.rdx + q - 1)) * __ldg(ax.rdxh + q);
-                return ((r - c) * __ldg(ax.rdxh + q + 1) - (c - l) * __ldg(ax.rdxh + q)) * __ldg(ax.rdxc + q);
-            } else {
-                double dxl, dxr;
-                if (!center) {
-                    dxl = __ldg(ax.dx + q - 1);
-                    dxr = __ldg(ax.dx + q);
-                } else {
-                    dxl = P::mul(P::add(__ldg(ax.dx + q - 1), __ldg(ax.dx + q)), 0.5);
-                    dxr = P::mul(P::add(__ldg(ax.dx + q), __ldg(ax.dx + q + 1)), 0.5);
-                }
-                const double dxc = P::mul(P::add(dxl, dxr), 0.5);
-                return P::div(P::sub(P::div(P::sub(r, c), dxr), P::div(P::sub(c, l), dxl)), dxc);
-            }
+        OPF_STENCIL_HEAD(-1, 1)
+        OPF_EVAL_BEGIN
+            return d2c_math<P>(TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), (a.loc[B] >> D) & 1, acc);
+        }
+        OPF_EV_BEGIN
+            return d2c_math<P>(TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), (a.loc[B] >> D) & 1, acc);
         }
     };
 
     // D1FirstOrderCentered<d>::eval (D1FirstOrderCentered.hpp:31-36); result loc flipped in prepare (:46)
     template <int D, class E>
     struct D1C {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const bool center = (a.loc[B] >> D) & 1;
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double c = E::template eval<B + 1, P, A0>(a, i, j, k);
-            if (center) {
-                const double l = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-                return P::mul(P::div(P::sub(c, l), P::add(__ldg(ax.dx + q - 1), __ldg(ax.dx + q))), 2.0);
-            } else {
-                const double r = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-                return P::div(P::sub(r, c), __ldg(ax.dx + q));
-            }
+        OPF_STENCIL_HEAD(-1, 1)
+        OPF_EVAL_BEGIN
+            if ((a.loc[B] >> D) & 1) return P::mul(P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), P::add(acc.template dx<-1>(), acc.template dx<0>())), 2.0);
+            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), acc.template dx<0>());
+        }
+        OPF_EV_BEGIN
+            if ((a.loc[B] >> D) & 1) return P::mul(P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), P::add(acc.template dx<-1>(), acc.template dx<0>())), 2.0);
+            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), acc.template dx<0>());
         }
     };
 
     // D1FirstOrderBiasedDownwind<d>::eval (D1FirstOrderBiasedDownwind.hpp:53-57)
     template <int D, class E>
     struct D1Dn {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const bool center = (a.loc[B] >> D) & 1;
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double c = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double l = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-            const double h = center ? P::mul(P::add(__ldg(ax.dx + q - 1), __ldg(ax.dx + q)), 0.5) : __ldg(ax.dx + q - 1);
-            return P::div(P::sub(c, l), h);
+        OPF_STENCIL_HEAD(-1, 0)
+        OPF_EVAL_BEGIN
+            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<-1>(), acc.template dx<0>()), 0.5) : acc.template dx<-1>();
+            return P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), h);
+        }
+        OPF_EV_BEGIN
+            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<-1>(), acc.template dx<0>()), 0.5) : acc.template dx<-1>();
+            return P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), h);
         }
     };
     // D1FirstOrderBiasedUpwind<d>::eval (D1FirstOrderBiasedUpwind.hpp:54-58)
     template <int D, class E>
     struct D1Up {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const bool center = (a.loc[B] >> D) & 1;
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double r = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-            const double c = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double h = center ? P::mul(P::add(__ldg(ax.dx + q), __ldg(ax.dx + q + 1)), 0.5) : __ldg(ax.dx + q);
-            return P::div(P::sub(r, c), h);
+        OPF_STENCIL_HEAD(0, 1)
+        OPF_EVAL_BEGIN
+            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<0>(), acc.template dx<1>()), 0.5) : acc.template dx<0>();
+            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), h);
+        }
+        OPF_EV_BEGIN
+            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<0>(), acc.template dx<1>()), 0.5) : acc.template dx<0>();
+            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), h);
         }
     };
 
@@ -314,84 +463,89 @@ namespace opf {
             return P::add(P::add(P::mul(w1, ddx1), P::mul(w2, ddx2)), P::mul(w3, ddx3));
         }
     }
-
-    // D1WENO53Downwind<d>::eval (D1WENO53Downwind.hpp:77-86): taps i-3..i+2, h = dx(d,i) ("uniform mesh is assumed")
+    // one-sided differences divided by h = dx(d,i) ("uniform mesh is assumed", D1WENO53Upwind.hpp:76)
+    template <class P, class Acc>
+    __device__ __forceinline__ double weno53(double a0, double a1, double a2, double a3, double a4, double a5, const Acc& m) {
+        if constexpr (P::fast) {
+            const double rh = m.template rdx<0>();
+            return weno53_core<P>((a1 - a0) * rh, (a2 - a1) * rh, (a3 - a2) * rh, (a4 - a3) * rh, (a5 - a4) * rh);
+        } else {
+            const double h = m.template dx<0>();
+            return weno53_core<P>(P::div(P::sub(a1, a0), h), P::div(P::sub(a2, a1), h), P::div(P::sub(a3, a2), h),
+                                  P::div(P::sub(a4, a3), h), P::div(P::sub(a5, a4), h));
+        }
+    }
+    // D1WENO53Downwind<d>::eval (D1WENO53Downwind.hpp:77-86): taps i-3..i+2;  d1=(pm2-pm3)/h ... d5=(pp2-pp1)/h
     template <int D, class E>
     struct WenoDn {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double pm3 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -3));
-            const double pm2 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -2));
-            const double pm1 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-            const double p0 = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double pp1 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-            const double pp2 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 2));
-            if constexpr (P::fast) {
-                const double rh = __ldg(ax.rdx + q);
-                return weno53_core<P>((pm2 - pm3) * rh, (pm1 - pm2) * rh, (p0 - pm1) * rh, (pp1 - p0) * rh, (pp2 - pp1) * rh);
-            } else {
-                const double h = __ldg(ax.dx + q);
-                return weno53_core<P>(P::div(P::sub(pm2, pm3), h), P::div(P::sub(pm1, pm2), h), P::div(P::sub(p0, pm1), h),
-                                      P::div(P::sub(pp1, p0), h), P::div(P::sub(pp2, pp1), h));
-            }
+        OPF_STENCIL_HEAD(-3, 2)
+        OPF_EVAL_BEGIN
+            return weno53<P>(TAP(IC<-3>{}), TAP(IC<-2>{}), TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), TAP(IC<2>{}), acc);
+        }
+        OPF_EV_BEGIN
+            return weno53<P>(TAP(IC<-3>{}), TAP(IC<-2>{}), TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), TAP(IC<2>{}), acc);
         }
     };
-    // D1WENO53Upwind<d>::eval (D1WENO53Upwind.hpp:75-84): taps i-2..i+3
+    // D1WENO53Upwind<d>::eval (D1WENO53Upwind.hpp:75-84): taps i-2..i+3;  d1=(pp3-pp2)/h ... d5=(pm1-pm2)/h, i.e. the
+    // same differences with the sequence reversed and negated twice: d_k = (b_k - b_{k+1})/h with b = (pp3,...,pm2)
+    template <class P, class Acc>
+    __device__ __forceinline__ double weno53_up(double pm2, double pm1, double p0, double pp1, double pp2, double pp3, const Acc& m) {
+        if constexpr (P::fast) {
+            const double rh = m.template rdx<0>();
+            return weno53_core<P>((pp3 - pp2) * rh, (pp2 - pp1) * rh, (pp1 - p0) * rh, (p0 - pm1) * rh, (pm1 - pm2) * rh);
+        } else {
+            const double h = m.template dx<0>();
+            return weno53_core<P>(P::div(P::sub(pp3, pp2), h), P::div(P::sub(pp2, pp1), h), P::div(P::sub(pp1, p0), h),
+                                  P::div(P::sub(p0, pm1), h), P::div(P::sub(pm1, pm2), h));
+        }
+    }
     template <int D, class E>
     struct WenoUp {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double pm2 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -2));
-            const double pm1 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-            const double p0 = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double pp1 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-            const double pp2 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 2));
-            const double pp3 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 3));
-            if constexpr (P::fast) {
-                const double rh = __ldg(ax.rdx + q);
-                return weno53_core<P>((pp3 - pp2) * rh, (pp2 - pp1) * rh, (pp1 - p0) * rh, (p0 - pm1) * rh, (pm1 - pm2) * rh);
-            } else {
-                const double h = __ldg(ax.dx + q);
-                return weno53_core<P>(P::div(P::sub(pp3, pp2), h), P::div(P::sub(pp2, pp1), h), P::div(P::sub(pp1, p0), h),
-                                      P::div(P::sub(p0, pm1), h), P::div(P::sub(pm1, pm2), h));
-            }
+        OPF_STENCIL_HEAD(-2, 3)
+        OPF_EVAL_BEGIN
+            return weno53_up<P>(TAP(IC<-2>{}), TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), TAP(IC<2>{}), TAP(IC<3>{}), acc);
+        }
+        OPF_EV_BEGIN
+            return weno53_up<P>(TAP(IC<-2>{}), TAP(IC<-1>{}), TAP(IC<0>{}), TAP(IC<1>{}), TAP(IC<2>{}), TAP(IC<3>{}), acc);
         }
     };
 
     // D1Linear<d, Cen2Cor>::eval (D1Linear.hpp:36-42) with Interpolator1D::intp (Interpolator.hpp:21-23,38-40)
+    template <class P, class Acc>
+    __device__ __forceinline__ double intp_c2n(double y1, double y2, const Acc& m) {
+        const double x1 = P::add(m.template x<-1>(), P::mul(0.5, m.template dx<-1>()));
+        const double x2 = P::add(m.template x<0>(), P::mul(0.5, m.template dx<0>()));
+        const double x = m.template x<0>();
+        const double u1 = P::sub(x1, x), u2 = P::sub(x2, x);
+        return P::div(P::sub(P::mul(u1, y2), P::mul(u2, y1)), P::sub(u1, u2));
+    }
     template <int D, class E>
     struct IntpC2N {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const int q = axis_of<D>(i, j, k);
-            const AxisView& ax = a.ax[D];
-            const double x1 = P::add(__ldg(ax.x + q - 1), P::mul(0.5, __ldg(ax.dx + q - 1)));
-            const double x2 = P::add(__ldg(ax.x + q), P::mul(0.5, __ldg(ax.dx + q)));
-            const double y1 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, -1));
-            const double y2 = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double x = __ldg(ax.x + q);
-            const double u1 = P::sub(x1, x), u2 = P::sub(x2, x);
-            return P::div(P::sub(P::mul(u1, y2), P::mul(u2, y1)), P::sub(u1, u2));
+        OPF_STENCIL_HEAD(-1, 0)
+        OPF_EVAL_BEGIN
+            return intp_c2n<P>(TAP(IC<-1>{}), TAP(IC<0>{}), acc);
+        }
+        OPF_EV_BEGIN
+            return intp_c2n<P>(TAP(IC<-1>{}), TAP(IC<0>{}), acc);
         }
     };
     // D1Linear<d, Cor2Cen>::eval (D1Linear.hpp:44): Math::mid (Interpolator.hpp:83)
     template <int D, class E>
     struct IntpN2C {
-        static constexpr int size = 1 + E::size, maxaxis = (D > E::maxaxis ? D : E::maxaxis), nf = E::nf;
-        template <int B, class P, bool A0>
-        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
-            const double y1 = E::template eval<B + 1, P, A0>(a, i, j, k);
-            const double y2 = E::template eval<B + 1, P, A0>(a, OPF_SHIFT(D, 1));
-            return P::mul(P::add(y1, y2), 0.5);
+        OPF_STENCIL_HEAD(0, 1)
+        OPF_EVAL_BEGIN
+            (void) acc;
+            return P::mul(P::add(TAP(IC<0>{}), TAP(IC<1>{})), 0.5);
+        }
+        OPF_EV_BEGIN
+            (void) acc;
+            (void) a;
+            return P::mul(P::add(TAP(IC<0>{}), TAP(IC<1>{})), 0.5);
         }
     };
+#undef OPF_STENCIL_HEAD
+#undef OPF_EVAL_BEGIN
+#undef OPF_EV_BEGIN
 
     // ------------------------------------------------------------------------------------------- skeletons
     // compound assignment (BasicArithOp, Constants.hpp:53; FieldAssigner.hpp:48-80).  `op` is warp-uniform.
@@ -442,6 +596,595 @@ namespace opf {
                 if (op != 0) v = apply_op<P>(op, oldp[o], v);
                 dst.p[o] = v;
             }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------- register-window skeleton
+    // K1, fast path.  Each thread owns CX consecutive cells along axis 0 and marches along the slowest axis.  For every
+    // field slot the thread keeps a *register window*: the rows (cross offset dc, march offset dm) the expression taps
+    // (known at compile time from E::taps), each CX + halo wide.  Per march step only the leading row of every column is
+    // loaded -- 128-bit vector loads for the aligned core -- and the window is rotated in registers, so a 7-point
+    // stencil issues 3 vector loads + 2 scalar halo loads per CX cells instead of 7 scalar loads per cell.
+    template <int LO, int HI, class Fn>
+    __device__ __forceinline__ void static_for(Fn&& fn) {
+        if constexpr (LO <= HI) {
+            fn(IC<LO>{});
+            static_for<LO + 1, HI>(fn);
+        }
+    }
+
+    template <class E, bool A0, int DIM>
+    struct WinInfo {
+        static constexpr int NS = A0 ? 1 : (E::nf > 0 ? E::nf : 1);
+        static constexpr TapSet<NS> make() {
+            TapSet<NS> ts;
+            E::template taps<A0>(ts, tap_origin());
+            return ts;
+        }
+        static constexpr TapSet<NS> ts = make();
+        static constexpr bool overflow = ts.overflow;
+        // (cross, march) -> (dj, dk): 3-D marches along k with cross axis j; 2-D marches along j
+        __host__ __device__ static constexpr int dj_of(int dc, int dm) { return DIM == 3 ? dc : dm; }
+        __host__ __device__ static constexpr int dk_of(int dc, int dm) { return DIM == 3 ? dm : 0; }
+        __host__ __device__ static constexpr bool tap(int s, int di, int dc, int dm) {
+            const int dj = dj_of(dc, dm), dk = dk_of(dc, dm);
+            if (di < -WR || di > WR || dj < -WR || dj > WR || dk < -WR || dk > WR) return false;
+            return ts.g[s].t[dk + WR][dj + WR][di + WR];
+        }
+        // column (s, dc): march extent and x extent over the whole column
+        __host__ __device__ static constexpr bool col_used(int s, int dc) {
+            for (int dm = -WR; dm <= WR; ++dm)
+                for (int di = -WR; di <= WR; ++di)
+                    if (tap(s, di, dc, dm)) return true;
+            return false;
+        }
+        __host__ __device__ static constexpr int col_mlo(int s, int dc) {
+            for (int dm = -WR; dm <= WR; ++dm)
+                for (int di = -WR; di <= WR; ++di)
+                    if (tap(s, di, dc, dm)) return dm;
+            return 0;
+        }
+        __host__ __device__ static constexpr int col_mhi(int s, int dc) {
+            for (int dm = WR; dm >= -WR; --dm)
+                for (int di = -WR; di <= WR; ++di)
+                    if (tap(s, di, dc, dm)) return dm;
+            return 0;
+        }
+        __host__ __device__ static constexpr int col_xlo(int s, int dc) {
+            for (int di = -WR; di <= 0; ++di)
+                for (int dm = -WR; dm <= WR; ++dm)
+                    if (tap(s, di, dc, dm)) return di;
+            return 0;
+        }
+        __host__ __device__ static constexpr int col_xhi(int s, int dc) {
+            for (int di = WR; di >= 0; --di)
+                for (int dm = -WR; dm <= WR; ++dm)
+                    if (tap(s, di, dc, dm)) return di;
+            return 0;
+        }
+        __host__ __device__ static constexpr int bound(int which) {// 0 xlo 1 xhi 2 clo 3 chi 4 mlo 5 mhi over all slots
+            int v = 0;
+            for (int s = 0; s < NS; ++s)
+                for (int dc = -WR; dc <= WR; ++dc) {
+                    if (!col_used(s, dc)) continue;
+                    if (which == 0) v = col_xlo(s, dc) < v ? col_xlo(s, dc) : v;
+                    if (which == 1) v = col_xhi(s, dc) > v ? col_xhi(s, dc) : v;
+                    if (which == 2) v = dc < v ? dc : v;
+                    if (which == 3) v = dc > v ? dc : v;
+                    if (which == 4) v = col_mlo(s, dc) < v ? col_mlo(s, dc) : v;
+                    if (which == 5) v = col_mhi(s, dc) > v ? col_mhi(s, dc) : v;
+                }
+            return v;
+        }
+        static constexpr int XL = bound(0), XH = bound(1), CL = bound(2), CH = bound(3), ML = bound(4), MH = bound(5);
+        // per-thread staging ring (cp.async): every used column contributes CX/2 16-byte core pairs and its halo doubles
+        __host__ __device__ static constexpr int halo_count(int s, int dc) { return col_xhi(s, dc) - col_xlo(s, dc); }
+        __host__ __device__ static constexpr int col_index(int s, int dc) {// running index of used columns before (s,dc)
+            int n = 0;
+            for (int ss = 0; ss < NS; ++ss)
+                for (int d = -WR; d <= WR; ++d) {
+                    if (ss == s && d == dc) return n;
+                    if (col_used(ss, d)) ++n;
+                }
+            return n;
+        }
+        __host__ __device__ static constexpr int halo_off(int s, int dc) {
+            int n = 0;
+            for (int ss = 0; ss < NS; ++ss)
+                for (int d = -WR; d <= WR; ++d) {
+                    if (ss == s && d == dc) return n;
+                    if (col_used(ss, d)) n += halo_count(ss, d);
+                }
+            return n;
+        }
+        static constexpr int NCOLS = col_index(NS, -WR - 1), NHALO = halo_off(NS, -WR - 1);
+        // cross offsets only exist in 3-D
+        static constexpr bool ok = !overflow && (DIM == 3 || DIM == 2);
+    };
+
+    template <class E, bool A0, int DIM, int CX>
+    struct WinCtx {
+        using WI = WinInfo<E, A0, DIM>;
+        const ExprArgs& a;
+        int i0, j, k;
+        unsigned valign;
+        double w[WI::NS][WI::MH - WI::ML + 2][WI::CH - WI::CL + 1][CX + WI::XH - WI::XL];// +1 march slot: prefetched row
+        // mesh coefficients in registers: [array][offset + CR] relative to i0 (axis 0), the cross index and the march
+        // index.  Every entry is loaded by load_coefs*(); entries no stencil node reads are dead code for the compiler.
+        // (mesh arrays carry 16 doubles of slack on both sides so even a not-eliminated load stays in bounds)
+        static constexpr int CR = WR + 2;
+        double cf0[5][CX + 2 * CR], cfc[5][2 * CR + 1], cfm[5][2 * CR + 1];
+
+        __device__ __forceinline__ WinCtx(const ExprArgs& a_, unsigned va) : a(a_), i0(0), j(0), k(0), valign(va) {}
+
+        static constexpr int MAXIS = DIM - 1;               // march axis
+        static constexpr int CAXIS = DIM == 3 ? 1 : -1;     // cross axis (3-D only)
+        __device__ __forceinline__ static const double* arr_of(const AxisView& ax, int which) {
+            return which == CF_X ? ax.x : (which == CF_DX ? ax.dx : (which == CF_RDX ? ax.rdx : (which == CF_RDXH ? ax.rdxh : ax.rdxc)));
+        }
+        template <int D, int ARR, int O>
+        __device__ __forceinline__ double coef() const {
+            if constexpr (D == 0) return cf0[ARR][O + CR];
+            else if constexpr (D == MAXIS) return cfm[ARR][O + CR];
+            else return cfc[ARR][O + CR];
+        }
+        __device__ __forceinline__ void load_coefs_fixed() {// axis 0 and the cross axis: loop invariant
+#pragma unroll
+            for (int arr = 0; arr < 5; ++arr) {
+                const double* p0 = arr_of(a.ax[0], arr) + i0;
+#pragma unroll
+                for (int o = -CR; o < CX + CR; ++o) cf0[arr][o + CR] = __ldg(p0 + o);
+                if constexpr (CAXIS >= 0) {
+                    const double* pc = arr_of(a.ax[CAXIS], arr) + j;
+#pragma unroll
+                    for (int o = -CR; o <= CR; ++o) cfc[arr][o + CR] = __ldg(pc + o);
+                }
+            }
+        }
+        __device__ __forceinline__ void load_coefs_march(int m) {// warp-uniform addresses
+#pragma unroll
+            for (int arr = 0; arr < 5; ++arr) {
+                const double* pm = arr_of(a.ax[MAXIS], arr) + m;
+#pragma unroll
+                for (int o = -CR; o <= CR; ++o) cfm[arr][o + CR] = __ldg(pm + o);
+            }
+        }
+
+        template <int S, int DI, int DJ, int DK>
+        __device__ __forceinline__ double get() const {
+            constexpr int dc = DIM == 3 ? DJ : 0, dm = DIM == 3 ? DK : DJ;
+            static_assert(DIM == 3 || DK == 0, "2-D expression taps axis 2");
+            return w[S][dm - WI::ML][dc - WI::CL][DI - WI::XL];
+        }
+
+        // load row (S, DC, DM) of the window at the current (i0, j, k)
+        template <int S, int DC, int DM>
+        __device__ __forceinline__ void load_row() {
+            constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC);
+            constexpr int dj = WI::dj_of(DC, DM), dk = WI::dk_of(DC, DM);
+            const FieldView& v = a.f[S];
+            const double* rp = v.p + ((long long) i0 + (long long) (j + dj) * v.s1 + (long long) (k + dk) * v.s2);
+            double* row = w[S][DM - WI::ML][DC - WI::CL];
+            if ((valign >> S) & 1) {
+#pragma unroll
+                for (int c = 0; c < CX; c += 2) {
+                    const double2 t = __ldg(reinterpret_cast<const double2*>(rp + c));
+                    row[c - WI::XL] = t.x;
+                    row[c + 1 - WI::XL] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CX; ++c) row[c - WI::XL] = __ldg(rp + c);
+            }
+#pragma unroll
+            for (int x = xlo; x < 0; ++x) row[x - WI::XL] = __ldg(rp + x);
+#pragma unroll
+            for (int x = CX; x <= CX - 1 + xhi; ++x) row[x - WI::XL] = __ldg(rp + x);
+        }
+
+        // prologue: rows [mlo, mhi] of every column at the first march index; steady state: prefetch row mhi+1 (the
+        // leading row of the NEXT march step) while the current step computes, then rotate the window down by one.
+        __device__ __forceinline__ void load_prologue() {
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) {
+                        static_for<WI::col_mlo(S, DC), WI::col_mhi(S, DC)>([&](auto dm) { load_row<S, DC, decltype(dm)::value>(); });
+                    }
+                });
+            });
+        }
+        __device__ __forceinline__ void prefetch_next() {
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) load_row<S, DC, WI::col_mhi(S, DC) + 1>();
+                });
+            });
+        }
+        // ---- cp.async staging ring: each thread copies the leading rows of a future march step straight from global
+        // to its PRIVATE shared-memory slots (no barrier needed: a thread only ever reads what it copied itself), so the
+        // DRAM latency of STAGES-1 march steps is hidden without spending registers.  Layout (conflict-free, lanes
+        // contiguous): pairs[stage][pair][thread] as double2, then halos[stage][halo][thread] as double.
+        // colp[ci]: pointer to element x = i0 of column ci's leading row for the NEXT march index to be staged; bumped
+        // by the march stride after every issue (no 64-bit multiplies in the loop)
+        __device__ __forceinline__ void init_colp(const double** colp, int mfirst) {
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) {
+                        constexpr int DM = WI::col_mhi(S, DC);
+                        const FieldView& v = a.f[S];
+                        const int jj = DIM == 3 ? j + DC : mfirst + DM, kk = DIM == 3 ? mfirst + DM : 0;
+                        colp[WI::col_index(S, DC)] = v.p + ((long long) i0 + (long long) jj * v.s1 + (long long) kk * v.s2);
+                    }
+                });
+            });
+        }
+        __device__ __forceinline__ void issue_stage(const double** colp, unsigned pair_sa, unsigned halo_sa, unsigned ntb) {
+            // pair_sa / halo_sa: shared-space byte addresses of this thread's first pair / halo slot of the target stage;
+            // ntb = threads per block * 8 bytes
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) {
+                        constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC);
+                        constexpr int ci = WI::col_index(S, DC), ho = WI::halo_off(S, DC);
+                        const double* rp = colp[ci];
+#pragma unroll
+                        for (int c = 0; c < CX; c += 2) {
+                            const unsigned d = pair_sa + (unsigned) (ci * (CX / 2) + c / 2) * 2u * ntb;
+                            if ((valign >> S) & 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(rp + c));
+                            else {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(rp + c));
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u), "l"(rp + c + 1));
+                            }
+                        }
+                        int h = 0;
+#pragma unroll
+                        for (int x = xlo; x < 0; ++x, ++h)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(halo_sa + (unsigned) (ho + h) * ntb), "l"(rp + x));
+#pragma unroll
+                        for (int x = CX; x <= CX - 1 + xhi; ++x, ++h)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(halo_sa + (unsigned) (ho + h) * ntb), "l"(rp + x));
+                        colp[ci] = rp + (DIM == 3 ? a.f[S].s2 : a.f[S].s1);
+                    }
+                });
+            });
+        }
+        // staged rows -> the window's prefetch slot (march offset mhi + 1)
+        __device__ __forceinline__ void consume_stage(const double2* pairs, const double* halos, int nt) {
+            // pairs / halos: this thread's first pair / halo slot of the stage
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) {
+                        constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC), DM = WI::col_mhi(S, DC) + 1;
+                        constexpr int ci = WI::col_index(S, DC), ho = WI::halo_off(S, DC);
+                        double* row = w[S][DM - WI::ML][DC - WI::CL];
+#pragma unroll
+                        for (int c = 0; c < CX; c += 2) {
+                            const double2 t = pairs[(ci * (CX / 2) + c / 2) * nt];
+                            row[c - WI::XL] = t.x;
+                            row[c + 1 - WI::XL] = t.y;
+                        }
+                        int h = 0;
+#pragma unroll
+                        for (int x = xlo; x < 0; ++x, ++h) row[x - WI::XL] = halos[(ho + h) * nt];
+#pragma unroll
+                        for (int x = CX; x <= CX - 1 + xhi; ++x, ++h) row[x - WI::XL] = halos[(ho + h) * nt];
+                    }
+                });
+            });
+        }
+        // L2 prefetch of the DRAM-unique stream: the leading row of the dc = 0 column of every slot, `pd` march steps
+        // ahead (one request per 128-byte line: lanes whose tile starts a line).  Costs no registers, unlike a deeper
+        // register pipeline, and turns the later vector load into an L2 hit.
+        __device__ __forceinline__ void prefetch_l2(int pd) {
+            static_for<0, WI::NS - 1>([&](auto s) {
+                constexpr int S = decltype(s)::value;
+                if constexpr (WI::col_used(S, 0)) {
+                    constexpr int dm = WI::col_mhi(S, 0);
+                    constexpr int dj = WI::dj_of(0, dm), dk = WI::dk_of(0, dm);
+                    const FieldView& v = a.f[S];
+                    const double* rp = v.p + ((long long) i0 + (long long) (j + dj + (DIM == 2 ? pd : 0)) * v.s1 +
+                                              (long long) (k + dk + (DIM == 3 ? pd : 0)) * v.s2);
+                    if ((reinterpret_cast<unsigned long long>(rp) & 127ull) < (unsigned long long) (CX * 8))
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                }
+            });
+        }
+        __device__ __forceinline__ void rotate() {
+            static_for<0, WI::NS - 1>([&](auto s) {
+                static_for<WI::CL, WI::CH>([&](auto dc) {
+                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
+                    if constexpr (WI::col_used(S, DC)) {
+                        constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC);
+                        static_for<WI::col_mlo(S, DC), WI::col_mhi(S, DC)>([&](auto dm) {
+                            constexpr int DM = decltype(dm)::value;
+#pragma unroll
+                            for (int x = xlo; x <= CX - 1 + xhi; ++x)
+                                w[S][DM - WI::ML][DC - WI::CL][x - WI::XL] = w[S][DM + 1 - WI::ML][DC - WI::CL][x - WI::XL];
+                        });
+                    }
+                });
+            });
+        }
+    };
+
+    template <class E, class P, bool A0, int DIM, int CX, bool HASOP, int STAGES>
+    __global__ void __launch_bounds__(128, OPF_WIN_MINBLOCKS) window_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
+                                                         const double* __restrict__ oldp, const LaunchRange r, const int ch,
+                                                         const int op, const unsigned valign, const int dalign, const int pd) {
+        using Ctx = WinCtx<E, A0, DIM, CX>;
+        const int i0 = r.lo[0] + (blockIdx.x * blockDim.x + threadIdx.x) * CX;
+        if (i0 >= r.hi[0]) return;
+        Ctx c(a, valign);
+        c.i0 = i0;
+        int m0, m1;// march range
+        if constexpr (DIM == 3) {
+            c.j = r.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+            if (c.j >= r.hi[1]) return;
+            m0 = r.lo[2] + blockIdx.z * ch;
+            m1 = min(m0 + ch, r.hi[2]);
+            c.k = m0;
+        } else {
+            m0 = r.lo[1] + blockIdx.y * ch;
+            m1 = min(m0 + ch, r.hi[1]);
+            c.j = m0;
+            c.k = 0;
+        }
+        const bool full = i0 + CX <= r.hi[0];
+        c.load_coefs_fixed();
+        c.load_prologue();
+        // staging ring in dynamic shared memory (STAGES > 1), private per thread
+        extern __shared__ double2 opf_ring[];
+        using WI = typename Ctx::WI;
+        const int nt = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+        constexpr int NPAIR = WI::NCOLS * (CX / 2) > 0 ? WI::NCOLS * (CX / 2) : 1, NHAL = WI::NHALO > 0 ? WI::NHALO : 1;
+        const double2* pairs = opf_ring + tid;                                                       // + stage * NPAIR * nt
+        const double* halos = reinterpret_cast<const double*>(opf_ring + (long long) STAGES * NPAIR * nt) + tid;// + stage * NHAL * nt
+        const unsigned pair_sa = (unsigned) __cvta_generic_to_shared(pairs), halo_sa = (unsigned) __cvta_generic_to_shared(halos);
+        const unsigned ntb = (unsigned) nt * 8u, pstride = NPAIR * 2u * ntb, hstride = NHAL * ntb;
+        const double* colp[WI::NCOLS > 0 ? WI::NCOLS : 1];
+        if constexpr (STAGES > 1) {
+            c.init_colp(colp, m0 + 1);
+#pragma unroll
+            for (int sidx = 0; sidx < STAGES - 1; ++sidx) {
+                if (m0 + 1 + sidx < m1) c.issue_stage(colp, pair_sa + sidx * pstride, halo_sa + sidx * hstride, ntb);
+                asm volatile("cp.async.commit_group;");
+            }
+        }
+        int stage = 0;// stage holding march index m + 1
+        for (int m = m0; m < m1; ++m) {
+            if constexpr (DIM == 3) c.k = m;
+            else
+                c.j = m;
+            if constexpr (STAGES > 1) {
+                // refill the slot consumed last step with march index m + STAGES, then wait for m + 1
+                const int fill = stage == 0 ? STAGES - 1 : stage - 1;
+                if (m + STAGES < m1) c.issue_stage(colp, pair_sa + fill * pstride, halo_sa + fill * hstride, ntb);
+                asm volatile("cp.async.commit_group;");
+                asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+                if (m + 1 < m1) c.consume_stage(pairs + (long long) stage * NPAIR * nt, halos + (long long) stage * NHAL * nt, nt);
+                stage = stage + 1 == STAGES ? 0 : stage + 1;
+            } else {
+                if (m + 1 < m1) c.prefetch_next();// in flight during this step's arithmetic
+            }
+            if (pd > 0 && m + pd < r.hi[DIM - 1]) c.prefetch_l2(pd);
+            c.load_coefs_march(m);
+            double out[CX];
+            static_for<0, CX - 1>([&](auto cc) { out[decltype(cc)::value] = E::template ev<0, P, A0, decltype(cc)::value, 0, 0>(c); });
+            const long long o = (long long) i0 + (long long) c.j * dst.s1 + (long long) c.k * dst.s2;
+            if constexpr (HASOP) {
+#pragma unroll
+                for (int x = 0; x < CX; ++x)
+                    if (full || i0 + x < r.hi[0]) out[x] = apply_op<P>(op, oldp[o + x], out[x]);
+            }
+            if (full && dalign) {
+#pragma unroll
+                for (int x = 0; x < CX; x += 2) *reinterpret_cast<double2*>(dst.p + o + x) = make_double2(out[x], out[x + 1]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < CX; ++x)
+                    if (i0 + x < r.hi[0]) dst.p[o + x] = out[x];
+            }
+            c.rotate();
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------- TMA tile skeleton (3-D)
+    // K1, sm_100a path for 3-D fields.  A block owns a (BX*CX) x BY tile of the x-y plane and marches along z.  One elected
+    // thread streams whole tile-plus-halo planes of every field slot into a shared-memory ring with TMA
+    // (cp.async.bulk.tensor.3d, completion on an mbarrier); all threads evaluate the functor with every tap served from
+    // shared memory at compile-time offsets.  Loads cost no registers and no LSU instructions, out-of-range halo cells
+    // are zero-filled by the TMA unit, and the ring depth (planes in flight) hides HBM latency independent of occupancy.
+    extern "C" int opf_internal_tensor_map(void* out128, const void* base, const unsigned long long* dims,
+                                           const unsigned long long* strides_b, const unsigned* box, int rank);
+
+    __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    }
+    __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+        asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "OPF_WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra OPF_DONE_%=;\n"
+                "bra OPF_WAIT_%=;\n"
+                "OPF_DONE_%=:\n"
+                "}\n" ::"r"(smem_u32(bar)),
+                "r"(parity)
+                : "memory");
+    }
+    __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                             smem_u32(smem)),
+                     "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+                     : "memory");
+    }
+
+    template <int NS>
+    struct alignas(64) TmaMaps {
+        CUtensorMap m[NS];
+        int org[NS][3];
+    };
+
+    template <class E, bool A0, int CX, int BX, int BY>
+    struct TmaGeom {
+        using WI = WinInfo<E, A0, 3>;
+        static constexpr int HXL = (-WI::XL + 1) / 2 * 2, HXH = (WI::XH + 1) / 2 * 2;// even halos keep pairs 16-byte aligned
+        static constexpr int BW = BX * CX + HXL + HXH;                               // box width (doubles), even
+        static constexpr int HYL = -WI::CL, HYH = WI::CH, BH = BY + HYL + HYH;
+        static constexpr int NPL = WI::MH - WI::ML + 1;// planes a cell taps
+        static constexpr int TILE_B = (BW * BH * 8 + 127) / 128 * 128;
+        static constexpr int NS = WI::NS;
+    };
+
+    template <class E, bool A0, int CX, int BX, int BY>
+    struct TmaCtx {
+        using G = TmaGeom<E, A0, CX, BX, BY>;
+        using WI = typename G::WI;
+        const ExprArgs& a;
+        int i0, j, k;
+        const double* pl[G::NS][G::NPL];// this thread's centre element (x = i0) in every tapped plane of every slot
+        static constexpr int CR = WR + 2;
+        double cf0[5][CX + 2 * CR], cfc[5][2 * CR + 1], cfm[5][2 * CR + 1];
+        __device__ __forceinline__ TmaCtx(const ExprArgs& a_) : a(a_), i0(0), j(0), k(0) {}
+        __device__ __forceinline__ static const double* arr_of(const AxisView& ax, int which) {
+            return which == CF_X ? ax.x : (which == CF_DX ? ax.dx : (which == CF_RDX ? ax.rdx : (which == CF_RDXH ? ax.rdxh : ax.rdxc)));
+        }
+        template <int D, int ARR, int O>
+        __device__ __forceinline__ double coef() const {
+            if constexpr (D == 0) return cf0[ARR][O + CR];
+            else if constexpr (D == 2) return cfm[ARR][O + CR];
+            else return cfc[ARR][O + CR];
+        }
+        __device__ __forceinline__ void load_coefs_fixed() {
+#pragma unroll
+            for (int arr = 0; arr < 5; ++arr) {
+                const double* p0 = arr_of(a.ax[0], arr) + i0;
+#pragma unroll
+                for (int o = -CR; o < CX + CR; ++o) cf0[arr][o + CR] = __ldg(p0 + o);
+                const double* pc = arr_of(a.ax[1], arr) + j;
+#pragma unroll
+                for (int o = -CR; o <= CR; ++o) cfc[arr][o + CR] = __ldg(pc + o);
+            }
+        }
+        __device__ __forceinline__ void load_coefs_march(int m) {
+#pragma unroll
+            for (int arr = 0; arr < 5; ++arr) {
+                const double* pm = arr_of(a.ax[2], arr) + m;
+#pragma unroll
+                for (int o = -CR; o <= CR; ++o) cfm[arr][o + CR] = __ldg(pm + o);
+            }
+        }
+        template <int S, int DI, int DJ, int DK>
+        __device__ __forceinline__ double get() const {
+            return pl[S][DK - WI::ML][DJ * G::BW + DI];
+        }
+    };
+
+    template <class E, class P, bool A0, int CX, int BX, int BY, int STAGES, bool HASOP>
+    __global__ void __launch_bounds__(BX* BY) tma_kernel(const __grid_constant__ ExprArgs a,
+                                                         const __grid_constant__ TmaMaps<TmaGeom<E, A0, CX, BX, BY>::NS> maps, const DstView dst,
+                                                         const double* __restrict__ oldp, const LaunchRange r, const int ch, const int op,
+                                                         const int dalign) {
+        using G = TmaGeom<E, A0, CX, BX, BY>;
+        using WI = typename G::WI;
+        using Ctx = TmaCtx<E, A0, CX, BX, BY>;
+        constexpr int NS = G::NS, NPL = G::NPL;
+        static_assert(STAGES > NPL, "ring must hold the tapped planes plus at least one plane in flight");
+        extern __shared__ __align__(128) unsigned char opf_tma_smem[];
+        unsigned long long* full = reinterpret_cast<unsigned long long*>(opf_tma_smem);// [STAGES]
+        unsigned char* ring = opf_tma_smem + 128;                                       // [STAGES][NS] tiles of TILE_B bytes
+        const int tid = threadIdx.y * BX + threadIdx.x;
+        const int x0 = r.lo[0] + blockIdx.x * (BX * CX), y0 = r.lo[1] + blockIdx.y * BY;
+        const int m0 = r.lo[2] + blockIdx.z * ch, m1 = min(m0 + ch, r.hi[2]);
+        const int pfirst = m0 + WI::ML, plast = m1 - 1 + WI::MH;// planes this block touches
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        auto issue = [&](int plane, int stage) {// elected thread: one box per slot, all completing on full[stage]
+            mbar_expect_tx(&full[stage], (unsigned) (NS * G::BW * G::BH * 8));
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                tma_load_3d(ring + (size_t) (stage * NS + s) * G::TILE_B, &maps.m[s], &full[stage], x0 - G::HXL - maps.org[s][0],
+                            y0 - G::HYL - maps.org[s][1], plane - maps.org[s][2]);
+        };
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s)
+                if (pfirst + s <= plast) issue(pfirst + s, s);
+        }
+        Ctx c(a);
+        c.i0 = x0 + threadIdx.x * CX;
+        c.j = y0 + threadIdx.y;
+        const bool active = c.i0 < r.hi[0] && c.j < r.hi[1];
+        const bool full_tile = c.i0 + CX <= r.hi[0];
+        if (active) c.load_coefs_fixed();
+        // byte offset of this thread's centre element inside a tile
+        const int toff = ((threadIdx.y + G::HYL) * G::BW + G::HXL + threadIdx.x * CX) * 8;
+        // wait for the planes the first step taps except the newest one (waited inside the loop)
+        int s_lo = 0;             // stage holding plane m + ML
+        unsigned phase_bits = 0u; // bit s: parity to wait for on full[s]
+#pragma unroll
+        for (int q = 0; q < NPL - 1; ++q) {
+            mbar_wait(&full[q], 0u);
+        }
+        for (int q = 0; q < NPL - 1; ++q) phase_bits ^= 1u << q;
+        for (int m = m0; m < m1; ++m) {
+            c.k = m;
+            // newest tapped plane m + MH lives in stage (s_lo + NPL - 1) % STAGES
+            int s_new = s_lo + NPL - 1;
+            if (s_new >= STAGES) s_new -= STAGES;
+            mbar_wait(&full[s_new], (phase_bits >> s_new) & 1u);
+            phase_bits ^= 1u << s_new;
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    int st = s_lo + q;
+                    if (st >= STAGES) st -= STAGES;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        c.pl[s][q] = reinterpret_cast<const double*>(ring + (size_t) (st * NS + s) * G::TILE_B + toff);
+                }
+                c.load_coefs_march(m);
+                double out[CX];
+                static_for<0, CX - 1>([&](auto cc) { out[decltype(cc)::value] = E::template ev<0, P, A0, decltype(cc)::value, 0, 0>(c); });
+                const long long o = (long long) c.i0 + (long long) c.j * dst.s1 + (long long) m * dst.s2;
+                if constexpr (HASOP) {
+#pragma unroll
+                    for (int x = 0; x < CX; ++x)
+                        if (full_tile || c.i0 + x < r.hi[0]) out[x] = apply_op<P>(op, oldp[o + x], out[x]);
+                }
+                if (full_tile && dalign) {
+#pragma unroll
+                    for (int x = 0; x < CX; x += 2) *reinterpret_cast<double2*>(dst.p + o + x) = make_double2(out[x], out[x + 1]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < CX; ++x)
+                        if (c.i0 + x < r.hi[0]) dst.p[o + x] = out[x];
+                }
+            }
+            __syncthreads();// every thread is done with plane m + ML: its stage can be refilled
+            if (tid == 0) {
+                const int pnext = m + WI::ML + STAGES;
+                if (pnext <= plast) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(pnext, s_lo);
+                }
+            }
+            s_lo = s_lo + 1 == STAGES ? 0 : s_lo + 1;
         }
     }
 
@@ -544,6 +1287,70 @@ namespace opf {
         return g;
     }
 
+    template <class E, class P, bool A0, int DIM>
+    int launch_window(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
+        constexpr int CX = 2;
+        static const int ety = getenv("OPF_WTY") ? atoi(getenv("OPF_WTY")) : 0;
+        static const int etx = getenv("OPF_WTX") ? atoi(getenv("OPF_WTX")) : 0;
+        static const int ech = getenv("OPF_WCH") ? atoi(getenv("OPF_WCH")) : 0;
+        const int n0 = li.r.hi[0] - li.r.lo[0], n1 = li.r.hi[1] - li.r.lo[1], n2 = li.r.hi[2] - li.r.lo[2];
+        const int nt = (n0 + CX - 1) / CX;// thread tiles along x
+        int tx = etx > 0 ? etx : 32;
+        dim3 block, grid;
+        int ch;
+        if (DIM == 3) {
+            const int ty = ety > 0 ? ety : 128 / tx;
+            ch = ech > 0 ? ech : 64;
+            block = dim3(tx, ty, 1);
+            grid = dim3((nt + tx - 1) / tx, (n1 + ty - 1) / ty, (n2 + ch - 1) / ch);
+        } else {
+            tx = etx > 0 ? etx : (nt >= 128 ? 128 : (nt >= 64 ? 64 : 32));// <= 128 (launch bounds)
+            ch = ech > 0 ? ech : 64;
+            block = dim3(tx, 1, 1);
+            grid = dim3((nt + tx - 1) / tx, (n1 + ch - 1) / ch, 1);
+        }
+        static const int pd = getenv("OPF_WPD") ? atoi(getenv("OPF_WPD")) : 8;
+        static const int stages = getenv("OPF_WST") ? atoi(getenv("OPF_WST")) : 4;
+        using WI = WinInfo<E, A0, DIM>;
+        const int nthreads = block.x * block.y;
+        auto go = [&](auto kern, int st_count) {
+            const size_t smem = st_count > 1 ? (size_t) st_count * nthreads * ((WI::NCOLS * (CX / 2) > 0 ? WI::NCOLS * (CX / 2) : 1) * 16 + (WI::NHALO > 0 ? WI::NHALO : 1) * 8) : 0;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            kern<<<grid, block, smem, st>>>(a, li.dst, li.old, li.r, ch, li.op, li.valign, li.dalign, pd);
+            return (int) cudaGetLastError();
+        };
+        if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1>, 1);
+        if (stages >= 6) return go(window_kernel<E, P, A0, DIM, CX, false, 6>, 6);
+        if (stages >= 3) return go(window_kernel<E, P, A0, DIM, CX, false, 4>, 4);
+        return go(window_kernel<E, P, A0, DIM, CX, false, 1>, 1);
+    }
+
+    template <class E, class P, bool A0, int BY>
+    int launch_tma(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
+        constexpr int CX = 2, BX = 64;
+        using G = TmaGeom<E, A0, CX, BX, BY>;
+        constexpr int STAGES = G::NPL + 3;
+        static const int ech = getenv("OPF_TCH") ? atoi(getenv("OPF_TCH")) : 0;
+        TmaMaps<G::NS> maps;
+        for (int s = 0; s < G::NS; ++s) {
+            const auto& t = li.tma[s];
+            const unsigned box[3] = {(unsigned) G::BW, (unsigned) G::BH, 1u};
+            if (opf_internal_tensor_map(&maps.m[s], t.base, t.dim, t.stride_b, box, 3) != 0) return -3;
+            for (int d = 0; d < 3; ++d) maps.org[s][d] = t.org[d];
+        }
+        const int n0 = li.r.hi[0] - li.r.lo[0], n1 = li.r.hi[1] - li.r.lo[1], n2 = li.r.hi[2] - li.r.lo[2];
+        const int ch = ech > 0 ? ech : 64;
+        dim3 block(BX, BY, 1), grid((n0 + BX * CX - 1) / (BX * CX), (n1 + BY - 1) / BY, (n2 + ch - 1) / ch);
+        const size_t smem = 128 + (size_t) STAGES * G::NS * G::TILE_B;
+        auto go = [&](auto kern) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            kern<<<grid, block, smem, st>>>(a, maps, li.dst, li.old, li.r, ch, li.op, li.dalign);
+            return (int) cudaGetLastError();
+        };
+        if (li.op != 0) return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, true>);
+        return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, false>);
+    }
+
     template <class E, class P, bool A0>
     int launch_assign(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
         const LaunchGeom g = assign_geometry(li);
@@ -555,10 +1362,25 @@ namespace opf {
             }
         if constexpr (E::maxaxis < 2)
             if (li.dim == 2) {
+                if constexpr (WinInfo<E, A0, 2>::ok && E::nf > 0)
+                    if (li.window) return launch_window<E, P, A0, 2>(a, li, st);
                 assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
                 return (int) cudaGetLastError();
             }
         if (li.dim == 3) {
+            if constexpr (WinInfo<E, A0, 3>::ok && E::nf > 0) {
+                // TMA tile skeleton: footprint must fit the ring/box budget (<= 200 KB of shared memory)
+                static const int tma_on = getenv("OPF_TMA") ? atoi(getenv("OPF_TMA")) : 1;
+                static const int tby = getenv("OPF_TBY") ? atoi(getenv("OPF_TBY")) : 4;
+                using G4 = TmaGeom<E, A0, 2, 64, 4>;
+                using G8 = TmaGeom<E, A0, 2, 64, 8>;
+                if (tma_on && li.window && li.tma_ok && (li.r.hi[0] - li.r.lo[0]) >= 64) {
+                    if constexpr (128 + (G8::NPL + 3) * G8::NS * G8::TILE_B <= 200 * 1024)
+                        if (tby == 8) return launch_tma<E, P, A0, 8>(a, li, st);
+                    if constexpr (128 + (G4::NPL + 3) * G4::NS * G4::TILE_B <= 200 * 1024) return launch_tma<E, P, A0, 4>(a, li, st);
+                }
+                if (li.window) return launch_window<E, P, A0, 3>(a, li, st);
+            }
             assign_kernel<E, P, A0, 3><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
             return (int) cudaGetLastError();
         }
