@@ -328,14 +328,34 @@ namespace {
 
     // K4/K5.  One thread per ghost cell; all arithmetic with IEEE-rn intrinsics in the reference's
     // operation order so ghost values are bit-identical to CartesianField.hpp:379-629.
-    __global__ void __launch_bounds__(256) fill_kernel(const FillParams p) {
-        const long long n0 = p.hi[0] - p.lo[0], n1 = p.hi[1] - p.lo[1], n2 = p.hi[2] - p.lo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+    // several independent fill ops in one launch (both sides of an axis; all Corner-Dirichlet faces).  lww: "last
+    // writer wins" -- a cell also covered by a later op of the list is left to that op, which reproduces the
+    // sequential overwrite order of CartesianField.hpp:351-364 for pure writes.
+    struct MultiFill {
+        FillParams op[6];
+        long long start[7];
+        int n, lww;
+    };
+    __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ MultiFill mf) {
+        const long long total_all = mf.start[mf.n];
+        for (long long tt = blockIdx.x * (long long) blockDim.x + threadIdx.x; tt < total_all; tt += (long long) gridDim.x * blockDim.x) {
+            int oi = 0;
+            while (oi + 1 < mf.n && tt >= mf.start[oi + 1]) ++oi;
+            const FillParams& p = mf.op[oi];
+            const long long t = tt - mf.start[oi];
+            const long long n0 = p.hi[0] - p.lo[0], n1 = p.hi[1] - p.lo[1];
             int g[3];
             g[0] = p.lo[0] + (int) (t % n0);
             g[1] = p.lo[1] + (int) ((t / n0) % n1);
             g[2] = p.lo[2] + (int) (t / (n0 * n1));
+            if (mf.lww) {
+                bool later = false;
+                for (int q = oi + 1; q < mf.n; ++q) {
+                    const FillParams& o2 = mf.op[q];
+                    if (g[0] >= o2.lo[0] && g[0] < o2.hi[0] && g[1] >= o2.lo[1] && g[1] < o2.hi[1] && g[2] >= o2.lo[2] && g[2] < o2.hi[2]) later = true;
+                }
+                if (later) continue;
+            }
             const long long o = (long long) g[0] + (long long) g[1] * p.s1 + (long long) g[2] * p.s2;
             double bcv = p.bcv;
             if (p.face) bcv = p.face[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2];
@@ -401,10 +421,8 @@ namespace {
 }// namespace
 
 namespace opfe {
-    static int launch_fill(opf_field_s* f, const FillOp& op) {
-        const long long total = op.r.count();
-        if (total <= 0) return OPF_OK;
-        FillParams p;
+    static bool make_fill_params(opf_field_s* f, const FillOp& op, FillParams& p) {
+        if (op.r.count() <= 0) return false;
         p.u = f->biased(f->cur);
         p.s1 = f->pitch1;
         p.s2 = f->pitch2;
@@ -429,8 +447,23 @@ namespace opfe {
         opf::AxisView av = mesh_axis_view(f->mesh, op.axis);
         p.x = av.x;
         p.dx = av.dx;
+        return true;
+    }
+    // launches ops[b, e) as ONE kernel
+    static int launch_fill_group(opf_field_s* f, const std::vector<FillOp>& ops, size_t b, size_t e, int lww) {
+        MultiFill mf;
+        mf.n = 0;
+        mf.lww = lww;
+        mf.start[0] = 0;
+        for (size_t i = b; i < e && mf.n < 6; ++i) {
+            if (!make_fill_params(f, ops[i], mf.op[mf.n])) continue;
+            mf.start[mf.n + 1] = mf.start[mf.n] + ops[i].r.count();
+            mf.n++;
+        }
+        if (mf.n == 0) return OPF_OK;
+        const long long total = mf.start[mf.n];
         const int blocks = (int) std::min<long long>((total + 255) / 256, 8LL * ctx().sm_count);
-        fill_kernel<<<blocks, 256, 0, ctx().stream>>>(p);
+        fill_kernel<<<blocks, 256, 0, ctx().stream>>>(mf);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
         return OPF_OK;
@@ -541,13 +574,24 @@ namespace opfe {
     }
 
     int field_update_padding(opf_field_s* f) {
-        for (const auto& op : f->fill0)
-            if (int rc = launch_fill(f, op)) return rc;
-        for (const auto& op : f->fill1)
-            if (int rc = launch_fill(f, op)) return rc;
+        // step 0: all Corner-Dirichlet boundary faces in one launch (pure writes, last writer wins on shared edges)
+        if (!f->fill0.empty())
+            if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1)) return rc;
+        // step 1: one launch per axis (its two sides are independent; later axes read earlier axes' ghosts)
+        for (size_t i = 0; i < f->fill1.size();) {
+            size_t e = i + 1;
+            while (e < f->fill1.size() && f->fill1[e].axis == f->fill1[i].axis) ++e;
+            if (int rc = launch_fill_group(f, f->fill1, i, e, 0)) return rc;
+            i = e;
+        }
         if (f->split_map.size() <= 1) {
-            for (const auto& op : f->fill2)
-                if (int rc = launch_fill(f, op)) return rc;
+            // step 2: periodic copies, one launch per axis
+            for (size_t i = 0; i < f->fill2.size();) {
+                size_t e = i + 1;
+                while (e < f->fill2.size() && f->fill2[e].axis == f->fill2[i].axis) ++e;
+                if (int rc = launch_fill_group(f, f->fill2, i, e, 0)) return rc;
+                i = e;
+            }
         } else {
             if (int rc = halo_exchange(f)) return rc;
         }

@@ -1084,9 +1084,35 @@ namespace opf {
                 for (int o = -CR; o <= CR; ++o) cfm[arr][o + CR] = __ldg(pm + o);
             }
         }
+        // core[s][plane][row][c]: the thread's own CX cells of every tapped row, fetched once per march step with 128-bit
+        // conflict-free shared loads; only x-halo taps (DI outside [0, CX)) read shared memory individually
+        double core[G::NS][G::NPL][G::HYL + G::HYH + 1][CX];
+        __host__ __device__ static constexpr bool row_used(int s, int dj, int dk) {
+            for (int di = -WR; di <= WR; ++di)
+                if (WI::tap(s, di, dj, dk)) return true;
+            return false;
+        }
+        __device__ __forceinline__ void load_cores() {
+            static_for<0, G::NS - 1>([&](auto s) {
+                static_for<WI::ML, WI::MH>([&](auto dk) {
+                    static_for<WI::CL, WI::CH>([&](auto dj) {
+                        constexpr int S = decltype(s)::value, DK = decltype(dk)::value, DJ = decltype(dj)::value;
+                        if constexpr (row_used(S, DJ, DK)) {
+#pragma unroll
+                            for (int c = 0; c < CX; c += 2) {
+                                const double2 t = *reinterpret_cast<const double2*>(pl[S][DK - WI::ML] + DJ * G::BW + c);
+                                core[S][DK - WI::ML][DJ + G::HYL][c] = t.x;
+                                core[S][DK - WI::ML][DJ + G::HYL][c + 1] = t.y;
+                            }
+                        }
+                    });
+                });
+            });
+        }
         template <int S, int DI, int DJ, int DK>
         __device__ __forceinline__ double get() const {
-            return pl[S][DK - WI::ML][DJ * G::BW + DI];
+            if constexpr (DI >= 0 && DI < CX) return core[S][DK - WI::ML][DJ + G::HYL][DI];
+            else return pl[S][DK - WI::ML][DJ * G::BW + DI];
         }
     };
 
@@ -1158,6 +1184,7 @@ namespace opf {
                     for (int s = 0; s < NS; ++s)
                         c.pl[s][q] = reinterpret_cast<const double*>(ring + (size_t) (st * NS + s) * G::TILE_B + toff);
                 }
+                c.load_cores();
                 c.load_coefs_march(m);
                 double out[CX];
                 static_for<0, CX - 1>([&](auto cc) { out[decltype(cc)::value] = E::template ev<0, P, A0, decltype(cc)::value, 0, 0>(c); });
