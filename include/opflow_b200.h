@@ -171,6 +171,11 @@ int opf_expr_prepare(const char* signature, const opf_field_t* fields, int nfiel
  * evaluated first (the engine writes the twin buffer and swaps instead of copying). */
 int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields,
                const double* scalars, int nscalars);
+/* same, with flags: OPF_ASSIGN_NO_PADDING skips the trailing updatePadding() (solver work vectors whose ghosts are
+ * refreshed explicitly before the next operator application) */
+#define OPF_ASSIGN_NO_PADDING 1
+int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields,
+                  const double* scalars, int nscalars, int flags);
 /* rangeReduce(range, op, expr.evalAt) RangeFor.hpp:87-121 for a device expression; range==NULL: the expression's
  * local ∩ accessible range.  globalReduce (:125-135) = this + opf_comm_allreduce. */
 int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
@@ -211,6 +216,23 @@ typedef struct {            /* StructSolverParamsBase :39-51 + the per-solver fi
 } opf_solver_params;
 
 typedef struct { int niter; double relerr, abserr; } opf_solve_state; /* EqnSolveState EqnSolveHandler.hpp:17-25 */
+
+/* makeEqnSolveHandler(f, target, solver) -> HYPREEqnSolveHandler ctor + init() (HYPREEqnSolveHandler.hpp:44-117), matrix-free:
+ * the equation  lhs(e) == rhs  is given as two expression signatures.  `lhs` must be linear in the unknown e; the leaves of
+ * lhs that ARE the unknown are flagged in `unknown_mask` (bit k <=> field leaf k is e; their entries in lhs_fields are ignored).
+ * The operator is never assembled: A.p = lhs evaluated on p with the target's boundary conditions made homogeneous, and
+ * b = rhs - lhs(e = 0 with the real boundary data).  pin_value pins the first assignable cell exactly like the reference
+ * (HYPREEqnSolveHandler.hpp:145-163, StencilField.hpp:132).  Supported: type PCG / BICGSTAB / GMRES(=BICGSTAB) / JACOBI / PFMG
+ * (stand-alone geometric multigrid), precond NONE / JACOBI / PFMG. */
+opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, const opf_field_t* lhs_fields, int n_lhs_fields,
+                               const double* lhs_scalars, int n_lhs_scalars, unsigned unknown_mask,
+                               const opf_solver_params* params);
+/* EqnSolveHandler::solve() (HYPREEqnSolveHandler.hpp:190-209): evaluates rhs, solves, writes the solution into the target field
+ * and refreshes its padding (returnValues :181-188).  Initial guess = current target values (initx :119-123). */
+int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_t* rhs_fields, int n_rhs_fields,
+                     const double* rhs_scalars, int n_rhs_scalars, opf_solve_state* state);
+int opf_solver_levels(opf_solver_t s); /* number of multigrid levels built (1 = no hierarchy) */
+int opf_solver_destroy(opf_solver_t s);
 
 #ifdef __cplusplus
 }

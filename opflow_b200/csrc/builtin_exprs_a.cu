@@ -33,3 +33,7 @@ OPF_BUILTIN(Cond<Gt<F<0>, S<0>>, F<1>, F<2>>)
 OPF_BUILTIN(Max<F<0>, F<1>>)
 OPF_BUILTIN(Min<F<0>, S<0>>)
 
+
+// ---- solver vector kernels (engine_solver.cu): weighted-Jacobi update, diagonal scaling
+OPF_BUILTIN(Mul<S<0>, Mul<F<0>, F<1>>>)
+OPF_BUILTIN(Add<F<0>, Mul<S<0>, Mul<F<1>, F<2>>>>)

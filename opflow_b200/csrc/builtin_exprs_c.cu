@@ -20,6 +20,11 @@ OPF_BUILTIN(Add<F<0>, Mul<S<0>, Add<Add<D2C<0, F<1>>, D2C<1, F<2>>>, D2C<2, F<3>
 // Laplacian (benchmark/Core/LaplaceOp.cpp:80 shape) and the Poisson operator of LidDriven (LidDriven2D.cpp:70)
 OPF_BUILTIN(Add<D2C<0, F<0>>, D2C<1, F<1>>>)
 OPF_BUILTIN(Add<Add<D2C<0, F<0>>, D2C<1, F<1>>>, D2C<2, F<2>>>)
+// fused residual r = b - L(x) of the Poisson operator (engine_solver.cu)
+OPF_BUILTIN(Sub<F<0>, Add<D2C<0, F<1>>, D2C<1, F<2>>>>)
+OPF_BUILTIN(Sub<F<0>, Add<Add<D2C<0, F<1>>, D2C<1, F<2>>>, D2C<2, F<3>>>>)
+// 1-D Poisson / Helmholtz pieces
+OPF_BUILTIN(Sub<F<0>, D2C<0, F<1>>>)
 
 // ---- examples/CONV1D/CONV1D.cpp:29-31 (BASELINE config C3)
 OPF_BUILTIN(Sub<F<0>, Mul<S<0>, D1Dn<0, F<1>>>>)

@@ -311,6 +311,28 @@ namespace opfe {
         for (int c = 0; c < n.nchild; ++c) footprint(t, n.child[c], l, h, lo, hi, used, mlo, mhi);
     }
 
+    // largest stencil reach of an expression along any axis (sum of the reaches of nested stencil operators)
+    static int node_radius(const Tree& t, int id) {
+        const Node& n = t.nodes[id];
+        int own = 0;
+        switch (n.kind) {
+            case K_D2C: case K_D1C: case K_D1DN: case K_D1UP: case K_INTPC2N: case K_INTPN2C: own = 1; break;
+            case K_WENODN: case K_WENOUP: own = 3; break;
+            default: own = 0;
+        }
+        int sub = 0;
+        for (int c = 0; c < n.nchild; ++c) sub = std::max(sub, node_radius(t, n.child[c]));
+        return own + sub;
+    }
+    int signature_radius(const char* sig) {
+        Tree t;
+        std::string k;
+        for (const char* p = sig; *p; ++p)
+            if (*p != ' ') k.push_back(*p);
+        if (parse_signature(k.c_str(), t)) return 1;
+        return std::max(1, node_radius(t, 0));
+    }
+
     // ------------------------------------------------------------------------------------------ registry
     struct Registry {
         std::mutex mu;
@@ -525,6 +547,11 @@ int opf_expr_prepare(const char* signature, const opf_field_t* fields, int nfiel
 
 int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
                int nscalars) {
+    return opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0);
+}
+
+int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
+                  int nscalars, int flags) {
     if (!dst || !signature) return fail(OPF_ERR_INVALID, "null argument");
     if (op < 0 || op > 4) return fail(OPF_ERR_UNSUPPORTED, "assign op %d is integer-only in the reference (Mod/And/Or/Xor/Shift)", op);
     if (int rc = require_device()) return rc;
@@ -592,6 +619,7 @@ int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t
         ctx().launches++;
     }
     if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep
+    if (flags & OPF_ASSIGN_NO_PADDING) return OPF_OK;
     return field_update_padding(dst);// CartesianField.hpp:231
 }
 
@@ -602,9 +630,10 @@ int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src) {
     return opf_assign(dst, op, "F<0>", fs, 1, nullptr, 0);
 }
 
-int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
-               const opf_range* range, double* result) {
-    if (!signature || !result) return fail(OPF_ERR_INVALID, "null argument");
+// launches the reduction; the result is left in device memory (*dev_result), valid until the next reduction on the stream
+static int reduce_launch(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
+                         const opf_range* range, double** dev_result, bool* empty) {
+    if (!signature) return fail(OPF_ERR_INVALID, "null argument");
     if (rop < 0 || rop > 4) return fail(OPF_ERR_INVALID, "bad reduce op");
     if (int rc = require_device()) return rc;
     Plan* p;
@@ -618,10 +647,8 @@ int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nf
     int alias0 = 0;
     if (int rc = fill_args(*p, fields, nfields, scalars, nscalars, r, fields[0]->mesh, a, alias0)) return rc;
     Context& c = ctx();
-    if (r.count() <= 0) {
-        *result = rop == OPF_RED_MAX ? -INFINITY : (rop == OPF_RED_MIN ? INFINITY : 0.0);
-        return OPF_OK;
-    }
+    *empty = r.count() <= 0;
+    if (*empty) return OPF_OK;
     opf::LaunchInfo li;
     memset(&li, 0, sizeof li);
     for (int d = 0; d < 3; ++d) {
@@ -639,10 +666,35 @@ int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nf
     const int rc = p->fn(&a, &li, c.stream);
     if (rc != 0) return fail(OPF_ERR_CUDA, "reduce launch of '%s' failed", p->sig.c_str());
     c.launches += 2;
-    OPF_CUDA(cudaMemcpyAsync(c.red_host, c.red_buf + li.n_partials, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    *dev_result = c.red_buf + li.n_partials;
+    return OPF_OK;
+}
+
+int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
+               const opf_range* range, double* result) {
+    if (!result) return fail(OPF_ERR_INVALID, "null argument");
+    double* dev = nullptr;
+    bool empty = false;
+    if (int rc = reduce_launch(rop, signature, fields, nfields, scalars, nscalars, range, &dev, &empty)) return rc;
+    if (empty) {
+        *result = rop == OPF_RED_MAX ? -INFINITY : (rop == OPF_RED_MIN ? INFINITY : 0.0);
+        return OPF_OK;
+    }
+    Context& c = ctx();
+    OPF_CUDA(cudaMemcpyAsync(c.red_host, dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     OPF_CUDA(cudaStreamSynchronize(c.stream));
     *result = c.red_host[0];
     return OPF_OK;
 }
 
 }// extern "C"
+
+namespace opfe {
+    // device-resident sum of a field over a box (no host synchronisation): used by the multigrid mean projection
+    int reduce_sum_device(opf_field_s* f, const Range& r, double** dev_result) {
+        opf_field_t F[1] = {f};
+        opf_range cr = to_c(r);
+        bool empty = false;
+        return reduce_launch(OPF_RED_SUM, "F<0>", F, 1, nullptr, 0, &cr, dev_result, &empty);
+    }
+}// namespace opfe

@@ -1,2 +1,782 @@
-// engine_solver.cu -- matrix-free implicit path (placeholder until the solver lands in this file).
+// engine_solver.cu -- the implicit path, matrix-free on the device.
+//
+// Reference: HYPREEqnSolveHandler (src/Core/Equation/HYPREEqnSolveHandler.hpp:50-231) evaluates the user's equation on a
+// symbolic StencilField, pushes every matrix row into a HYPRE Struct matrix through host SetValues calls and re-creates /
+// re-sets-up the HYPRE solver on every solve().  Here nothing is assembled: the operator of  lhs(e) == rhs  is applied by
+// running the *same device functor* the explicit path uses, on a work vector whose ghost cells are filled with the
+// target's boundary conditions made homogeneous (A.p = lhs(G_h(p))), and b = rhs - lhs(G(0)) carries the boundary data.
+// Krylov: PCG (HYPRE_StructPCG*, StructSolverPCG.hpp:25-96) and BiCGSTAB (StructSolverBiCGSTAB.hpp) -- the latter also
+// serves GMRES requests.  Preconditioner / stand-alone solver: geometric multigrid V-cycle (PFMG's role,
+// StructSolverPFMG.hpp:36-110) with weighted-Jacobi relaxation, full coarsening, operators re-discretised on the coarse
+// meshes by the same functor, full-weighting / averaging restriction and linear / constant prolongation chosen per axis
+// from the unknown's LocOnMesh; or plain Jacobi (StructSolverJacobi.hpp).  Dot products: warp-shuffle reductions (+ NCCL
+// allreduce when the field is decomposed).
 #include "engine.hpp"
+#include <algorithm>
+#include <cmath>
+
+namespace opfe {
+    int signature_radius(const char* sig);// engine_expr.cu
+    int reduce_sum_device(opf_field_s* f, const Range& r, double** dev_result);
+}
+using namespace opfe;
+
+namespace {
+    struct XferParams {
+        double* fine;
+        long long fs1, fs2;
+        double* coarse;
+        long long cs1, cs2;
+        int dim;
+        int flo[3], fhi[3];// fine writable range
+        int clo[3], chi[3];// coarse writable range
+        int f0[3], c0[3];  // accessible.start of fine / coarse (index origin of the 2:1 map)
+        int center[3], periodic[3], fper[3], cper[3];
+        int bclo[3], bchi[3];// opf_bctype of the unknown per axis side (cell-centred prolongation at the walls)
+    };
+
+    __device__ __forceinline__ bool in_box(const int* g, const int* lo, const int* hi) {
+        return g[0] >= lo[0] && g[0] < hi[0] && g[1] >= lo[1] && g[1] < hi[1] && g[2] >= lo[2] && g[2] < hi[2];
+    }
+
+    // per-axis prolongation weight of coarse cell I for fine cell i (cell-centred axes), shared by both transfer kernels so
+    // that R = (1/2) P^T per axis exactly (a symmetric V-cycle is what lets it precondition CG)
+    __device__ __forceinline__ double cc_weight(const XferParams& p, int d, int i, int I) {
+        const int r = i - p.f0[d];
+        const int par = p.c0[d] + (r >> 1);
+        int nb = (r & 1) ? par + 1 : par - 1;
+        bool wall = false;
+        if (p.periodic[d]) {
+            if (nb < p.c0[d]) nb += p.cper[d];
+            else if (nb >= p.c0[d] + p.cper[d])
+                nb -= p.cper[d];
+        } else if (nb < p.clo[d] || nb >= p.chi[d]) {
+            wall = true;
+        }
+        if (I == par) {
+            if (!wall) return 0.75;
+            const int bt = nb < p.clo[d] ? p.bclo[d] : p.bchi[d];
+            return (bt == OPF_BC_DIRC || bt == OPF_BC_ASYMM) ? 0.5 : 1.0;
+        }
+        if (!wall && I == nb) return 0.25;
+        return 0.0;
+    }
+
+    // coarse = R fine with R = (1/2) P^T per axis: node-centred (1/4, 1/2, 1/4) full weighting; cell-centred
+    // (1/8, 3/8, 3/8, 1/8) over fine cells 2I-1 .. 2I+2 (wall-adjusted like the prolongation).
+    __global__ void __launch_bounds__(256) restrict_kernel(const XferParams p) {
+        const long long n0 = p.chi[0] - p.clo[0], n1 = p.chi[1] - p.clo[1], n2 = p.chi[2] - p.clo[2];
+        const long long total = n0 * n1 * n2;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            int I[3] = {p.clo[0] + (int) (t % n0), p.clo[1] + (int) ((t / n0) % n1), p.clo[2] + (int) (t / (n0 * n1))};
+            int idx[3][4], cnt[3];
+            double wgt[3][4];
+            for (int d = 0; d < 3; ++d) {
+                if (d >= p.dim) {
+                    idx[d][0] = 0, cnt[d] = 1, wgt[d][0] = 1.0;
+                } else if (p.center[d]) {
+                    cnt[d] = 4;
+                    for (int a = 0; a < 4; ++a) {
+                        int i = p.f0[d] + 2 * (I[d] - p.c0[d]) - 1 + a;
+                        if (p.periodic[d]) {
+                            if (i < p.f0[d]) i += p.fper[d];
+                            else if (i >= p.f0[d] + p.fper[d])
+                                i -= p.fper[d];
+                        }
+                        idx[d][a] = i;
+                        wgt[d][a] = (i >= p.flo[d] && i < p.fhi[d]) ? 0.5 * cc_weight(p, d, i, I[d]) : 0.0;
+                    }
+                } else {
+                    cnt[d] = 3;
+                    for (int a = 0; a < 3; ++a) {
+                        int i = p.f0[d] + 2 * (I[d] - p.c0[d]) - 1 + a;
+                        if (p.periodic[d]) {
+                            if (i < p.f0[d]) i += p.fper[d];
+                            else if (i >= p.f0[d] + p.fper[d])
+                                i -= p.fper[d];
+                        }
+                        idx[d][a] = i;
+                        wgt[d][a] = a == 1 ? 0.5 : 0.25;
+                    }
+                }
+            }
+            double acc = 0.0;
+            for (int c = 0; c < cnt[2]; ++c)
+                for (int b = 0; b < cnt[1]; ++b)
+                    for (int a = 0; a < cnt[0]; ++a) {
+                        const int g[3] = {idx[0][a], idx[1][b], idx[2][c]};
+                        const double w = wgt[0][a] * wgt[1][b] * wgt[2][c];
+                        if (w == 0.0 || !in_box(g, p.flo, p.fhi)) continue;
+                        acc += w * p.fine[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2];
+                    }
+            p.coarse[(long long) I[0] + (long long) I[1] * p.cs1 + (long long) I[2] * p.cs2] = acc;
+        }
+    }
+
+    // fine += P coarse.  Linear interpolation per axis: node-centred (Corner) weights (1) / (1/2, 1/2); cell-centred (Center)
+    // weights (3/4 parent, 1/4 neighbouring coarse cell).  A neighbour beyond a wall is the homogeneous ghost value of the
+    // coarse correction: +parent for Neumann/Symm, -parent for Dirichlet/ASymm.
+    __global__ void __launch_bounds__(256) prolong_kernel(const XferParams p) {
+        const long long n0 = p.fhi[0] - p.flo[0], n1 = p.fhi[1] - p.flo[1], n2 = p.fhi[2] - p.flo[2];
+        const long long total = n0 * n1 * n2;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            int g[3] = {p.flo[0] + (int) (t % n0), p.flo[1] + (int) ((t / n0) % n1), p.flo[2] + (int) (t / (n0 * n1))};
+            int idx[3][2], cnt[3];
+            double wgt[3][2];
+            for (int d = 0; d < 3; ++d) {
+                if (d >= p.dim) {
+                    idx[d][0] = 0, cnt[d] = 1, wgt[d][0] = 1.0;
+                    continue;
+                }
+                const int r = g[d] - p.f0[d];
+                const int par = p.c0[d] + (r >> 1);
+                if (p.center[d]) {
+                    int nb = (r & 1) ? par + 1 : par - 1;
+                    if (p.periodic[d]) {
+                        if (nb < p.c0[d]) nb += p.cper[d];
+                        else if (nb >= p.c0[d] + p.cper[d])
+                            nb -= p.cper[d];
+                    }
+                    idx[d][0] = par, wgt[d][0] = cc_weight(p, d, g[d], par);
+                    idx[d][1] = nb, wgt[d][1] = cc_weight(p, d, g[d], nb), cnt[d] = wgt[d][1] != 0.0 ? 2 : 1;
+                } else if ((r & 1) == 0) {
+                    idx[d][0] = par, cnt[d] = 1, wgt[d][0] = 1.0;
+                } else {
+                    idx[d][0] = par, idx[d][1] = par + 1, cnt[d] = 2, wgt[d][0] = wgt[d][1] = 0.5;
+                    if (p.periodic[d] && idx[d][1] >= p.c0[d] + p.cper[d]) idx[d][1] -= p.cper[d];
+                }
+            }
+            double acc = 0.0;
+            for (int c = 0; c < cnt[2]; ++c)
+                for (int b = 0; b < cnt[1]; ++b)
+                    for (int a = 0; a < cnt[0]; ++a) {
+                        const int I[3] = {idx[0][a], idx[1][b], idx[2][c]};
+                        if (!in_box(I, p.clo, p.chi)) continue;
+                        acc += wgt[0][a] * wgt[1][b] * wgt[2][c] * p.coarse[(long long) I[0] + (long long) I[1] * p.cs1 + (long long) I[2] * p.cs2];
+                    }
+            p.fine[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2] += acc;
+        }
+    }
+
+    // probe vector for the diagonal: 1 on the cells whose index is congruent to `col` modulo m on every axis
+    struct Mod3 {
+        int m[3];
+    };
+    __global__ void __launch_bounds__(256) color_fill_kernel(double* u, long long s1, long long s2, opf::LaunchRange r, int dim, Mod3 mm, int c0, int c1,
+                                                             int c2) {
+        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
+        const long long total = n0 * n1 * n2;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            const int i = r.lo[0] + (int) (t % n0), j = r.lo[1] + (int) ((t / n0) % n1), k = r.lo[2] + (int) (t / (n0 * n1));
+            const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
+                            && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
+            u[(long long) i + (long long) j * s1 + (long long) k * s2] = on ? 1.0 : 0.0;
+        }
+    }
+    __global__ void __launch_bounds__(256) color_recip_kernel(const double* q, double* dinv, long long s1, long long s2, opf::LaunchRange r, int dim,
+                                                              Mod3 mm, int c0, int c1, int c2) {
+        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
+        const long long total = n0 * n1 * n2;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            const int i = r.lo[0] + (int) (t % n0), j = r.lo[1] + (int) ((t / n0) % n1), k = r.lo[2] + (int) (t / (n0 * n1));
+            const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
+                            && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
+            if (on) {
+                const long long o = (long long) i + (long long) j * s1 + (long long) k * s2;
+                const double d = q[o];
+                dinv[o] = d != 0.0 ? 1.0 / d : 0.0;
+            }
+        }
+    }
+    // u -= sum[0] / n over a box: projects a coarse right-hand side onto the range of a singular (all-Neumann / periodic)
+    // operator without a host round trip (sum[0] was produced by the reduction kernels on the same stream)
+    __global__ void __launch_bounds__(256) sub_mean_kernel(double* u, long long s1, long long s2, opf::LaunchRange r, const double* sum, double inv_n) {
+        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
+        const long long total = n0 * n1 * n2;
+        const double m = sum[0] * inv_n;
+        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+            const long long o = (r.lo[0] + t % n0) + (r.lo[1] + (t / n0) % n1) * s1 + (r.lo[2] + t / (n0 * n1)) * s2;
+            u[o] -= m;
+        }
+    }
+    __global__ void set_cell_kernel(double* u, long long off, double v) { u[off] = v; }
+    __global__ void copy_cell_kernel(double* dst, const double* src, long long off) { dst[off] = src[off]; }
+
+    int blocks_for(long long total) { return (int) std::max<long long>(1, std::min<long long>((total + 255) / 256, 8LL * ctx().sm_count)); }
+    opf::LaunchRange lr_of(const Range& r) {
+        opf::LaunchRange o;
+        for (int d = 0; d < 3; ++d) o.lo[d] = r.start[d], o.hi[d] = r.end[d];
+        return o;
+    }
+}// namespace
+
+struct opf_solver_s {
+    struct Level {
+        opf_mesh_s* mesh = nullptr;
+        opf_field_s *x = nullptr, *b = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
+        Range w;
+        long long pin_off = 0;// first assignable cell of this level (pinned on every level when the problem is pinned)
+    };
+    opf_field_s* target = nullptr;
+    std::string lhs_sig, res_sig;
+    std::vector<opf_field_s*> lhs_fields;
+    std::vector<double> lhs_scalars;
+    unsigned mask = 0;
+    opf_solver_params params{};
+    std::vector<Level> lv;
+    opf_field_s *X = nullptr, *B = nullptr, *R = nullptr, *P = nullptr, *Z = nullptr, *Q = nullptr;
+    opf_field_s *R0 = nullptr, *V = nullptr, *S = nullptr, *T = nullptr, *E0 = nullptr;// BiCGSTAB extras, boundary-data field
+    bool pinned = false;
+    long long pin_off = 0;
+    bool setup_done = false, mg = false, has_res_sig = false;
+    bool singular = false;  // pinned AND the operator annihilates constants (all-Neumann / periodic)
+    bool pin_active = false;// the Krylov-level operator currently carries the identity row of the pinned unknown
+    double omega = 0.8;
+};
+
+namespace {
+    using Solver = opf_solver_s;
+
+    opf_field_s* clone_homogeneous(opf_field_s* f, const char* name) {
+        opf_field_s* c = opf_field_clone(f, name);
+        if (!c) return nullptr;
+        for (int d = 0; d < c->dim; ++d)
+            for (int s = 0; s < 2; ++s) {
+                c->bc[d][s].value = 0.0;
+                if (c->bc[d][s].face_dev) {
+                    cudaFree(c->bc[d][s].face_dev);
+                    c->bc[d][s].face_dev = nullptr;
+                    c->bc[d][s].face.clear();
+                }
+            }
+        cudaMemsetAsync(c->buf[0], 0, sizeof(double) * c->elems, ctx().stream);
+        return c;
+    }
+
+    int assign(opf_field_s* dst, const char* sig, std::initializer_list<opf_field_s*> fs, std::initializer_list<double> sc) {
+        opf_field_t F[8];
+        double S[8];
+        int nf = 0, ns = 0;
+        for (auto f : fs) F[nf++] = f;
+        for (auto s : sc) S[ns++] = s;
+        return opf_assign_ex(dst, OPF_OP_EQ, sig, F, nf, S, ns, OPF_ASSIGN_NO_PADDING);
+    }
+    // q = lhs(in): ghost fill of `in` with its (homogeneous) BCs, then the expression functor
+    int apply_lhs(Solver* s, opf_field_s* in, opf_field_s* out, int level, bool pin = true) {
+        if (int rc = field_update_padding(in)) return rc;
+        opf_field_t F[OPF_MAX_FIELDS];
+        const int nf = (int) s->lhs_fields.size();
+        for (int k = 0; k < nf; ++k) F[k] = ((s->mask >> k) & 1u) ? in : s->lhs_fields[k];
+        if (int rc = opf_assign_ex(out, OPF_OP_EQ, s->lhs_sig.c_str(), F, nf, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING))
+            return rc;
+        if (s->pin_active && pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
+            copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(out->biased(out->cur), in->biased(in->cur), s->lv[level].pin_off);
+            ctx().launches++;
+        }
+        return OPF_OK;
+    }
+    // r = b - lhs(x)
+    int residual(Solver* s, opf_field_s* x, opf_field_s* b, opf_field_s* r, opf_field_s* scratch, int level, bool pin = true) {
+        if (s->has_res_sig && !(s->pin_active && pin)) {
+            if (int rc = field_update_padding(x)) return rc;
+            opf_field_t F[OPF_MAX_FIELDS];
+            const int nf = (int) s->lhs_fields.size();
+            F[0] = b;
+            for (int k = 0; k < nf; ++k) F[k + 1] = ((s->mask >> k) & 1u) ? x : s->lhs_fields[k];
+            return opf_assign_ex(r, OPF_OP_EQ, s->res_sig.c_str(), F, nf + 1, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING);
+        }
+        if (int rc = apply_lhs(s, x, scratch, level, pin)) return rc;
+        return assign(r, "Sub<F<0>,F<1>>", {b, scratch}, {});
+    }
+    int dot(Solver* s, opf_field_s* a, opf_field_s* b, const Range& w, double* out) {
+        opf_field_t F[2] = {a, b};
+        opf_range r = to_c(w);
+        if (int rc = opf_reduce(OPF_RED_SUM, "Mul<F<0>,F<1>>", F, 2, nullptr, 0, &r, out)) return rc;
+        if (s->target->n_ranks > 1 && comm_active()) return opf_comm_allreduce(out, 1, OPF_RED_SUM);
+        return OPF_OK;
+    }
+    void poke(opf_field_s* f, long long off, double v) {
+        set_cell_kernel<<<1, 1, 0, ctx().stream>>>(f->biased(f->cur), off, v);
+        ctx().launches++;
+    }
+
+    int build_diag(Solver* s, int level) {
+        auto& L = s->lv[level];
+        const int dim = s->target->dim;
+        const int m = 2 * signature_radius(s->lhs_sig.c_str()) + 1;
+        // probe colouring: cells closer than the stencil width must differ in colour, also across a periodic seam
+        Mod3 mm{{1, 1, 1}};
+        for (int d = 0; d < dim; ++d) {
+            mm.m[d] = m;
+            if (L.x->bc[d][0].type == OPF_BC_PERIODIC) {
+                const int per = L.x->accessible.end[d] - L.x->accessible.start[d];
+                while (per % mm.m[d] != 0 && per % mm.m[d] < m && mm.m[d] < per) mm.m[d]++;
+            }
+        }
+        const opf::LaunchRange r = lr_of(L.w);
+        const int nb = blocks_for(L.w.count());
+        for (int c2 = 0; c2 < mm.m[2]; ++c2)
+            for (int c1 = 0; c1 < mm.m[1]; ++c1)
+                for (int c0 = 0; c0 < mm.m[0]; ++c0) {
+                    color_fill_kernel<<<nb, 256, 0, ctx().stream>>>(L.x->biased(L.x->cur), L.x->pitch1, L.x->pitch2, r, dim, mm, c0, c1, c2);
+                    ctx().launches++;
+                    if (int rc = apply_lhs(s, L.x, L.q, level, false)) return rc;
+                    color_recip_kernel<<<nb, 256, 0, ctx().stream>>>(L.q->biased(L.q->cur), L.dinv->biased(L.dinv->cur), L.dinv->pitch1, L.dinv->pitch2, r,
+                                                                     dim, mm, c0, c1, c2);
+                    ctx().launches++;
+                }
+        OPF_CUDA(cudaGetLastError());
+        return assign(L.x, "S<0>", {}, {0.0});
+    }
+
+    int smooth(Solver* s, int level, int sweeps, bool zero_guess) {
+        auto& L = s->lv[level];
+        for (int it = 0; it < sweeps; ++it) {
+            if (it == 0 && zero_guess) {
+                if (int rc = assign(L.x, "Mul<S<0>,Mul<F<0>,F<1>>>", {L.dinv, L.b}, {s->omega})) return rc;
+            } else {
+                if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
+                if (int rc = assign(L.x, "Add<F<0>,Mul<S<0>,Mul<F<1>,F<2>>>>", {L.x, L.dinv, L.r}, {s->omega})) return rc;
+            }
+        }
+        return OPF_OK;
+    }
+
+    XferParams xfer(Solver* s, int lf) {
+        auto &Lf = s->lv[lf], &Lc = s->lv[lf + 1];
+        XferParams p{};
+        p.dim = s->target->dim;
+        for (int d = 0; d < 3; ++d) {
+            p.flo[d] = Lf.w.start[d], p.fhi[d] = Lf.w.end[d];
+            p.clo[d] = Lc.w.start[d], p.chi[d] = Lc.w.end[d];
+            p.f0[d] = Lf.x->accessible.start[d], p.c0[d] = Lc.x->accessible.start[d];
+            p.center[d] = d < p.dim ? (Lf.x->loc[d] == OPF_LOC_CENTER || Lf.x->bc[d][0].type == OPF_BC_PERIODIC) : 0;
+            p.periodic[d] = d < p.dim && Lf.x->bc[d][0].type == OPF_BC_PERIODIC;
+            p.bclo[d] = d < p.dim ? Lf.x->bc[d][0].type : 0;
+            p.bchi[d] = d < p.dim ? Lf.x->bc[d][1].type : 0;
+            p.fper[d] = Lf.x->accessible.end[d] - Lf.x->accessible.start[d];
+            p.cper[d] = Lc.x->accessible.end[d] - Lc.x->accessible.start[d];
+        }
+        // periodic Corner fields are node-based with period n-1: their 2:1 map is the vertex one
+        for (int d = 0; d < p.dim; ++d)
+            if (p.periodic[d] && Lf.x->loc[d] == OPF_LOC_CORNER) p.center[d] = 0;
+        return p;
+    }
+
+    // singular operators (the caller pinned a value: all-Neumann / periodic): keep every level's right-hand side in the
+    // range of the operator by removing its mean -- on the device, no host round trip
+    int project_mean(Solver* s, opf_field_s* f, const Range& w) {
+        double* dev = nullptr;
+        if (int rc = reduce_sum_device(f, w, &dev)) return rc;
+        sub_mean_kernel<<<blocks_for(w.count()), 256, 0, ctx().stream>>>(f->biased(f->cur), f->pitch1, f->pitch2, lr_of(w), dev, 1.0 / (double) w.count());
+        ctx().launches++;
+        return OPF_OK;
+    }
+
+    int vcycle(Solver* s, int level, bool zero_guess) {
+        auto& L = s->lv[level];
+        const int last = (int) s->lv.size() - 1;
+        if (s->singular)
+            if (int rc = project_mean(s, L.b, L.w)) return rc;
+        if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : 24, zero_guess);
+        const int pre = std::max(1, s->params.num_pre_relax), post = std::max(1, s->params.num_post_relax);
+        if (int rc = smooth(s, level, pre, zero_guess)) return rc;
+        if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
+        auto& C = s->lv[level + 1];
+        XferParams p = xfer(s, level);
+        p.fine = L.r->biased(L.r->cur), p.fs1 = L.r->pitch1, p.fs2 = L.r->pitch2;
+        p.coarse = C.b->biased(C.b->cur), p.cs1 = C.b->pitch1, p.cs2 = C.b->pitch2;
+        restrict_kernel<<<blocks_for(C.w.count()), 256, 0, ctx().stream>>>(p);
+        ctx().launches++;
+        if (int rc = vcycle(s, level + 1, true)) return rc;
+        p.fine = L.x->biased(L.x->cur), p.fs1 = L.x->pitch1, p.fs2 = L.x->pitch2;
+        p.coarse = C.x->biased(C.x->cur), p.cs1 = C.x->pitch1, p.cs2 = C.x->pitch2;
+        prolong_kernel<<<blocks_for(L.w.count()), 256, 0, ctx().stream>>>(p);
+        ctx().launches++;
+        OPF_CUDA(cudaGetLastError());
+        return smooth(s, level, post, false);
+    }
+
+    int project_mean(Solver* s, opf_field_s* f, const Range& w);
+    // z = M^-1 r
+    int precondition(Solver* s, opf_field_s* r, opf_field_s* z) {
+        auto& L0 = s->lv[0];
+        switch (s->params.precond) {
+            case OPF_SOLVER_PFMG:
+            case OPF_SOLVER_SMG: {
+                if (int rc = assign(L0.b, "F<0>", {r}, {})) return rc;
+                const int cycles = std::max(1, s->params.precond_max_iter);
+                for (int c = 0; c < cycles; ++c)
+                    if (int rc = vcycle(s, 0, c == 0)) return rc;
+                return assign(z, "F<0>", {L0.x}, {});
+            }
+            case OPF_SOLVER_JACOBI: return assign(z, "Mul<F<0>,F<1>>", {L0.dinv, r}, {});
+            default: return assign(z, "F<0>", {r}, {});
+        }
+    }
+    int precondition_pinned(Solver* s, opf_field_s* r, opf_field_s* z) {
+        if (int rc = precondition(s, r, z)) return rc;
+        if (s->pin_active) poke(z, s->pin_off, 0.0);// keep the pinned unknown out of the Krylov space (projection P M P)
+        else if (s->singular)
+            return project_mean(s, z, s->lv[0].w);// singular phase: stay in the mean-free subspace
+        return OPF_OK;
+    }
+
+    opf_field_s* make_level_field(opf_field_s* like, opf_mesh_s* mesh, const char* name) {
+        opf_field_desc d{};
+        d.mesh = mesh;
+        for (int a = 0; a < like->dim; ++a) {
+            d.loc[a] = like->loc[a];
+            for (int sd = 0; sd < 2; ++sd) {
+                d.bc[a][sd].type = like->bc[a][sd].type;
+                d.bc[a][sd].value = 0.0;
+                d.bc[a][sd].face = nullptr;
+                d.ext[a][sd] = like->ext[a][sd];
+            }
+        }
+        d.padding = like->padding;
+        d.n_ranks = 0;
+        return opf_field_create(&d, name);
+    }
+
+    int build_levels(Solver* s) {
+        opf_field_s* t = s->target;
+        const int dim = t->dim;
+        s->lv.clear();
+        Solver::Level L0;
+        L0.mesh = t->mesh;
+        L0.w = common(t->assignable, t->local);
+        L0.pin_off = (long long) t->assignable.start[0] + (long long) t->assignable.start[1] * t->pitch1 + (long long) t->assignable.start[2] * t->pitch2;
+        L0.x = clone_homogeneous(t, "mg.x0");
+        L0.b = clone_homogeneous(t, "mg.b0");
+        L0.r = clone_homogeneous(t, "mg.r0");
+        L0.q = clone_homogeneous(t, "mg.q0");
+        L0.dinv = clone_homogeneous(t, "mg.dinv0");
+        if (!L0.x || !L0.b || !L0.r || !L0.q || !L0.dinv) return OPF_ERR_CUDA;
+        s->lv.push_back(L0);
+        const bool want_mg = s->params.precond == OPF_SOLVER_PFMG || s->params.precond == OPF_SOLVER_SMG || s->params.type == OPF_SOLVER_PFMG
+                             || s->params.type == OPF_SOLVER_SMG;
+        // multigrid needs an operator that only involves the unknown (coefficient fields are not restricted yet) and a
+        // single-rank field
+        bool pure = true;
+        for (size_t k = 0; k < s->lhs_fields.size(); ++k)
+            if (!((s->mask >> k) & 1u)) pure = false;
+        s->mg = want_mg && pure && t->n_ranks <= 1;
+        if (!s->mg) return OPF_OK;
+        for (;;) {
+            auto& F = s->lv.back();
+            opf_mesh_s* fm = F.mesh;
+            bool ok = true;
+            int cd[3] = {1, 1, 1};
+            for (int d = 0; d < dim; ++d) {
+                const int n = fm->dims[d];
+                if ((n - 1) % 2 != 0 || (n - 1) / 2 < 2) ok = false;
+                cd[d] = (n - 1) / 2 + 1;
+            }
+            if (!ok || (int) s->lv.size() >= 16) break;
+            opf_mesh_s* cm = opf_mesh_create(dim, cd, fm->start, fm->pad_width);
+            for (int d = 0; d < dim; ++d) {
+                cm->ext_mode[d] = fm->ext_mode[d];
+                std::vector<double> xs(cd[d]);
+                const int off = fm->range.start[d] - fm->ext_range.start[d];
+                for (int i = 0; i < cd[d]; ++i) xs[i] = fm->ax[d].x[off + 2 * i];
+                if (int rc = opf_mesh_set_coords(cm, d, xs.data(), cd[d])) return rc;
+            }
+            Solver::Level C;
+            C.mesh = cm;
+            C.x = make_level_field(t, cm, "mg.x");
+            C.b = make_level_field(t, cm, "mg.b");
+            C.r = make_level_field(t, cm, "mg.r");
+            C.q = make_level_field(t, cm, "mg.q");
+            C.dinv = make_level_field(t, cm, "mg.dinv");
+            if (!C.x || !C.b || !C.r || !C.q || !C.dinv) return OPF_ERR_CUDA;
+            opf_mesh_destroy(cm);// fields hold their own references
+            C.w = common(C.x->assignable, C.x->local);
+            C.pin_off = (long long) C.x->assignable.start[0] + (long long) C.x->assignable.start[1] * C.x->pitch1
+                        + (long long) C.x->assignable.start[2] * C.x->pitch2;
+            if (C.w.count() <= 0) break;
+            s->lv.push_back(C);
+        }
+        return OPF_OK;
+    }
+
+    void free_level_fields(Solver::Level& L) {
+        for (opf_field_s* f : {L.x, L.b, L.r, L.q, L.dinv})
+            if (f) opf_field_destroy(f);
+    }
+}// namespace
+
+extern "C" {
+
+opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, const opf_field_t* lhs_fields, int n_lhs_fields,
+                               const double* lhs_scalars, int n_lhs_scalars, unsigned unknown_mask, const opf_solver_params* params) {
+    if (!target || !lhs_signature || !params || n_lhs_fields > OPF_MAX_FIELDS - 1) {
+        fail(OPF_ERR_INVALID, "opf_solver_create: bad arguments");
+        return nullptr;
+    }
+    if (require_device()) return nullptr;
+    switch (params->type) {
+        case OPF_SOLVER_PCG:
+        case OPF_SOLVER_BICGSTAB:
+        case OPF_SOLVER_GMRES:
+        case OPF_SOLVER_FGMRES:
+        case OPF_SOLVER_LGMRES:
+        case OPF_SOLVER_JACOBI:
+        case OPF_SOLVER_PFMG:
+        case OPF_SOLVER_SMG: break;
+        default: fail(OPF_ERR_UNSUPPORTED, "solver type %d is not implemented by the matrix-free engine", params->type); return nullptr;
+    }
+    auto* s = new opf_solver_s();
+    s->target = target;
+    s->lhs_sig = lhs_signature;
+    for (int k = 0; k < n_lhs_fields; ++k) s->lhs_fields.push_back(((unknown_mask >> k) & 1u) ? nullptr : lhs_fields[k]);
+    for (int k = 0; k < n_lhs_scalars; ++k) s->lhs_scalars.push_back(lhs_scalars[k]);
+    s->mask = unknown_mask;
+    s->params = *params;
+    if (s->params.tol <= 0) s->params.tol = 1e-6;// HYPRE default tolerance
+    if (s->params.max_iter <= 0) s->params.max_iter = 100;
+    s->omega = 2.0 * target->dim / (2.0 * target->dim + 1.0);// weighted Jacobi: 2/3, 4/5, 6/7
+    // fused residual kernel  r = b - lhs(x)  if that expression is compiled in: shift the leaf indices of lhs by one
+    {
+        std::string sh;
+        const std::string& g = s->lhs_sig;
+        for (size_t i = 0; i < g.size(); ++i) {
+            if (g[i] == 'F' && i + 1 < g.size() && g[i + 1] == '<' && (i == 0 || !isalnum((unsigned char) g[i - 1]))) {
+                size_t j = i + 2;
+                int v = 0;
+                while (j < g.size() && isdigit((unsigned char) g[j])) v = v * 10 + (g[j++] - '0');
+                sh += "F<" + std::to_string(v + 1);
+                i = j - 1;
+            } else if (g[i] != ' ')
+                sh.push_back(g[i]);
+        }
+        s->res_sig = "Sub<F<0>," + sh + ">";
+        s->has_res_sig = opf_expr_is_registered(s->res_sig.c_str()) != 0;
+    }
+    const Range w = common(target->assignable, target->local);
+    s->pinned = params->pin_value != 0;
+    s->pin_off = (long long) target->assignable.start[0] + (long long) target->assignable.start[1] * target->pitch1
+                 + (long long) target->assignable.start[2] * target->pitch2;
+    (void) w;
+    if (build_levels(s)) {
+        opf_solver_destroy(s);
+        return nullptr;
+    }
+    s->X = clone_homogeneous(target, "kry.x");
+    s->B = clone_homogeneous(target, "kry.b");
+    s->R = clone_homogeneous(target, "kry.r");
+    s->P = clone_homogeneous(target, "kry.p");
+    s->Z = clone_homogeneous(target, "kry.z");
+    s->Q = clone_homogeneous(target, "kry.q");
+    s->E0 = opf_field_clone(target, "kry.e0");
+    const bool bicg = params->type != OPF_SOLVER_PCG && params->type != OPF_SOLVER_JACOBI && params->type != OPF_SOLVER_PFMG && params->type != OPF_SOLVER_SMG;
+    if (bicg) {
+        s->R0 = clone_homogeneous(target, "kry.r0");
+        s->V = clone_homogeneous(target, "kry.v");
+        s->S = clone_homogeneous(target, "kry.s");
+        s->T = clone_homogeneous(target, "kry.t");
+    }
+    if (!s->X || !s->B || !s->R || !s->P || !s->Z || !s->Q || !s->E0) {
+        opf_solver_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+int opf_solver_levels(opf_solver_t s) { return s ? (int) s->lv.size() : -1; }
+
+int opf_solver_destroy(opf_solver_t s) {
+    if (!s) return OPF_OK;
+    for (auto& L : s->lv) free_level_fields(L);
+    for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0})
+        if (f) opf_field_destroy(f);
+    delete s;
+    return OPF_OK;
+}
+
+// one Krylov / stationary run on the current operator (s->pin_active), right-hand side s->B and iterate s->X
+static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm, double tol, int maxit, int* iters_io, double* rel_out) {
+    auto& L0 = s->lv[0];
+    double rnorm2 = 0;
+    int iters = *iters_io;
+    if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
+    if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
+    double rel = std::sqrt(rnorm2) / bnorm;
+    if (type == OPF_SOLVER_PCG) {
+        // preconditioned conjugate gradients, convergence on ||r||2 / ||b||2
+        double rz = 0, rz_new = 0, pq = 0;
+        if (rel > tol) {
+            if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
+            if (int rc = assign(s->P, "F<0>", {s->Z}, {})) return rc;
+            if (int rc = dot(s, s->R, s->Z, w, &rz)) return rc;
+        }
+        while (rel > tol && iters < maxit) {
+            if (int rc = apply_lhs(s, s->P, s->Q, 0)) return rc;
+            if (int rc = dot(s, s->P, s->Q, w, &pq)) return rc;
+            if (pq == 0.0) break;
+            const double alpha = rz / pq;
+            if (int rc = assign(s->X, "Add<F<0>,Mul<S<0>,F<1>>>", {s->X, s->P}, {alpha})) return rc;
+            if (int rc = assign(s->R, "Add<F<0>,Mul<S<0>,F<1>>>", {s->R, s->Q}, {-alpha})) return rc;
+            if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
+            ++iters;
+            rel = std::sqrt(rnorm2) / bnorm;
+            if (rel <= tol) break;
+            if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
+            if (int rc = dot(s, s->R, s->Z, w, &rz_new)) return rc;
+            const double beta = rz_new / rz;
+            rz = rz_new;
+            if (int rc = assign(s->P, "Add<F<0>,Mul<S<0>,F<1>>>", {s->Z, s->P}, {beta})) return rc;
+        }
+    } else if (type == OPF_SOLVER_JACOBI || type == OPF_SOLVER_PFMG || type == OPF_SOLVER_SMG) {
+        // stationary iteration: weighted Jacobi sweeps or V-cycles on the residual equation
+        while (rel > tol && iters < maxit) {
+            if (type == OPF_SOLVER_JACOBI) {
+                if (int rc = assign(s->X, "Add<F<0>,Mul<S<0>,Mul<F<1>,F<2>>>>", {s->X, L0.dinv, s->R}, {s->omega})) return rc;
+            } else {
+                if (int rc = assign(L0.b, "F<0>", {s->R}, {})) return rc;
+                if (int rc = vcycle(s, 0, true)) return rc;
+                if (int rc = assign(s->X, "Add<F<0>,F<1>>", {s->X, L0.x}, {})) return rc;
+            }
+            if (s->pin_active) poke(s->X, s->pin_off, 0.0);
+            if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
+            if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
+            ++iters;
+            rel = std::sqrt(rnorm2) / bnorm;
+        }
+    } else {
+        // right-preconditioned BiCGSTAB (also used for GMRES-family requests: non-symmetric operators)
+        double rho = 1, alpha = 1, omega = 1, rho_new = 0, r0v = 0, ts = 0, tt = 0;
+        if (int rc = assign(s->R0, "F<0>", {s->R}, {})) return rc;
+        if (int rc = assign(s->P, "S<0>", {}, {0.0})) return rc;
+        if (int rc = assign(s->V, "S<0>", {}, {0.0})) return rc;
+        while (rel > tol && iters < maxit) {
+            if (int rc = dot(s, s->R0, s->R, w, &rho_new)) return rc;
+            if (rho_new == 0.0) break;
+            const double beta = (rho_new / rho) * (alpha / omega);
+            rho = rho_new;
+            // p = r + beta (p - omega v)
+            if (int rc = assign(s->P, "Add<F<0>,Mul<S<0>,F<1>>>", {s->P, s->V}, {-omega})) return rc;
+            if (int rc = assign(s->P, "Add<F<0>,Mul<S<0>,F<1>>>", {s->R, s->P}, {beta})) return rc;
+            if (int rc = precondition_pinned(s, s->P, s->Z)) return rc;// z = M^-1 p
+            if (int rc = apply_lhs(s, s->Z, s->V, 0)) return rc;
+            if (int rc = dot(s, s->R0, s->V, w, &r0v)) return rc;
+            if (r0v == 0.0) break;
+            alpha = rho / r0v;
+            if (int rc = assign(s->S, "Add<F<0>,Mul<S<0>,F<1>>>", {s->R, s->V}, {-alpha})) return rc;
+            if (int rc = assign(s->X, "Add<F<0>,Mul<S<0>,F<1>>>", {s->X, s->Z}, {alpha})) return rc;
+            if (int rc = dot(s, s->S, s->S, w, &rnorm2)) return rc;
+            if (std::sqrt(rnorm2) / bnorm <= tol) {
+                ++iters;
+                rel = std::sqrt(rnorm2) / bnorm;
+                break;
+            }
+            if (int rc = precondition_pinned(s, s->S, s->Z)) return rc;// z = M^-1 s
+            if (int rc = apply_lhs(s, s->Z, s->T, 0)) return rc;
+            if (int rc = dot(s, s->T, s->S, w, &ts)) return rc;
+            if (int rc = dot(s, s->T, s->T, w, &tt)) return rc;
+            if (tt == 0.0) break;
+            omega = ts / tt;
+            if (int rc = assign(s->X, "Add<F<0>,Mul<S<0>,F<1>>>", {s->X, s->Z}, {omega})) return rc;
+            if (int rc = assign(s->R, "Add<F<0>,Mul<S<0>,F<1>>>", {s->S, s->T}, {-omega})) return rc;
+            if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
+            ++iters;
+            rel = std::sqrt(rnorm2) / bnorm;
+            if (omega == 0.0) break;
+        }
+    }
+    *iters_io = iters;
+    *rel_out = rel;
+    return OPF_OK;
+}
+
+int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_t* rhs_fields, int n_rhs_fields, const double* rhs_scalars,
+                     int n_rhs_scalars, opf_solve_state* state) {
+    if (!s || !rhs_signature) return fail(OPF_ERR_INVALID, "null argument");
+    opf_field_s* t = s->target;
+    const Range w = common(t->assignable, t->local);
+    // ---- setup (once when static_mat, else every solve -- the reference re-creates the HYPRE solver every time)
+    if (!s->setup_done || !s->params.static_mat) {
+        s->pin_active = false;
+        const bool need_diag = s->mg || s->params.precond == OPF_SOLVER_JACOBI || s->params.type == OPF_SOLVER_JACOBI || s->pinned;
+        if (need_diag)
+            for (int l = 0; l < (int) s->lv.size(); ++l)
+                if (l == 0 || s->mg)
+                    if (int rc = build_diag(s, l)) return rc;
+        if (s->pinned) {
+            // is the un-pinned operator singular with the constants as null space?  ||A.1||_inf vs ||diag||_inf
+            auto& L0 = s->lv[0];
+            double a1 = 0, dmin = 0;
+            if (int rc = assign(L0.x, "S<0>", {}, {1.0})) return rc;
+            if (int rc = apply_lhs(s, L0.x, L0.q, 0, false)) return rc;
+            opf_field_t F[1] = {L0.q};
+            opf_range cr = to_c(w);
+            if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &a1)) return rc;
+            F[0] = L0.dinv;
+            if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &dmin)) return rc;// max |1/d| = 1 / min |d|
+            if (int rc = assign(L0.x, "S<0>", {}, {0.0})) return rc;
+            s->singular = dmin > 0 && a1 * dmin <= 1e-8;
+        }
+        s->setup_done = true;
+    }
+    // ---- b = rhs - lhs(e = 0 with the real boundary data)          (generateAb / generateb :125-179: b = -bias)
+    s->pin_active = false;
+    if (int rc = opf_assign_ex(s->B, OPF_OP_EQ, rhs_signature, rhs_fields, n_rhs_fields, rhs_scalars, n_rhs_scalars, OPF_ASSIGN_NO_PADDING)) return rc;
+    if (int rc = assign(s->E0, "S<0>", {}, {0.0})) return rc;
+    if (int rc = apply_lhs(s, s->E0, s->Q, 0, false)) return rc;// E0 keeps the target's real BCs: its ghosts carry the boundary data
+    if (int rc = assign(s->B, "Sub<F<0>,F<1>>", {s->B, s->Q}, {})) return rc;
+    // ---- x0 = current target values (initx :119-123)
+    if (int rc = assign(s->X, "F<0>", {t}, {})) return rc;
+    double bnorm2 = 0;
+    if (int rc = dot(s, s->B, s->B, w, &bnorm2)) return rc;
+    const double bnorm = std::sqrt(bnorm2);
+    int iters = 0;
+    double rel = 0;
+    auto finish = [&](int rc_in) {
+        if (rc_in) return rc_in;
+        if (state) {
+            state->niter = iters;
+            state->relerr = rel;
+            state->abserr = rel * bnorm;
+        }
+        // returnValues (:181-188): x -> target, target.updatePadding()
+        return opf_field_assign_field(t, OPF_OP_EQ, s->X);
+    };
+    if (bnorm == 0.0) {
+        if (int rc = assign(s->X, "S<0>", {}, {0.0})) return rc;
+        return finish(OPF_OK);
+    }
+    const double tol = s->params.tol;
+    const int maxit = s->params.max_iter;
+    const int type = s->params.type;
+    if (s->pinned && s->singular) {
+        // Phase 1: the consistent singular system on the mean-free subspace (un-pinned operator, b made mean-free), whose
+        // solution shifted to x[pin] = 0 IS the reference's pinned solution whenever b is in the range of the operator.
+        if (int rc = project_mean(s, s->B, w)) return rc;
+        if (int rc = run_iteration(s, type, w, bnorm, tol, maxit, &iters, &rel)) return rc;
+        copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(s->Q->biased(s->Q->cur), s->X->biased(s->X->cur), s->pin_off);
+        sub_mean_kernel<<<blocks_for(w.count()), 256, 0, ctx().stream>>>(s->X->biased(s->X->cur), s->X->pitch1, s->X->pitch2, lr_of(w),
+                                                                         s->Q->biased(s->Q->cur) + s->pin_off, 1.0);
+        ctx().launches += 2;
+        // Phase 2: the reference's pinned system proper (row of the first assignable cell = identity, rhs 0).  For a consistent
+        // b it is already converged; an inconsistent b is polished with Jacobi-preconditioned iterations on the pinned operator.
+        s->pin_active = true;
+        poke(s->B, s->pin_off, 0.0);
+        const int saved_pre = s->params.precond;
+        s->params.precond = OPF_SOLVER_JACOBI;
+        const int ptype = (type == OPF_SOLVER_PCG || type == OPF_SOLVER_PFMG || type == OPF_SOLVER_SMG || type == OPF_SOLVER_JACOBI) ? OPF_SOLVER_PCG : type;
+        int rc = run_iteration(s, ptype, w, bnorm, tol, maxit, &iters, &rel);
+        s->params.precond = saved_pre;
+        s->pin_active = false;
+        return finish(rc);
+    }
+    if (s->pinned) {
+        s->pin_active = true;
+        poke(s->B, s->pin_off, 0.0);
+        poke(s->X, s->pin_off, 0.0);
+    }
+    int rc = run_iteration(s, type, w, bnorm, tol, maxit, &iters, &rel);
+    s->pin_active = false;
+    return finish(rc);
+}
+
+}// extern "C"

@@ -436,3 +436,75 @@ def set_mode(mode):
 
 def synchronize():
     check(lib().opf_synchronize())
+
+
+# ----------------------------------------------------------------------------------------------- implicit
+class Unknown(Expr):
+    """the `e` of the reference's equation lambda `[&](auto&& e) { return lhs(e) == rhs; }`"""
+
+    def __init__(self):
+        super().__init__("F")
+
+
+class StructSolverType:
+    NONE, Jacobi, SMG, PFMG, CYCRED, PCG, GMRES, FGMRES, LGMRES, BICGSTAB = range(10)
+
+
+class EqnSolveHandler:
+    """makeEqnSolveHandler(f, target, solver) (HYPREEqnSolveHandler.hpp:44-48) over the matrix-free C ABI.
+
+    f(e) must return (lhs, rhs) -- the two sides of the reference's `lhs == rhs`; lhs linear in e, rhs independent of e."""
+
+    def __init__(self, f, target: Field, type_=StructSolverType.PCG, precond=StructSolverType.NONE, tol=1e-10, maxIter=100,
+                 staticMat=False, pinValue=False, numPreRelax=1, numPostRelax=1, precondMaxIter=1):
+        e = Unknown()
+        self.target, self.e = target, e
+        self.lhs, self.rhs = f(e)
+        p = capi.SolverParams(type=type_, precond=precond, tol=tol, max_iter=maxIter, static_mat=int(staticMat), pin_value=int(pinValue),
+                              precond_tol=0.0, precond_max_iter=precondMaxIter, num_pre_relax=numPreRelax, num_post_relax=numPostRelax,
+                              relax_type=1, print_level=0)
+        sig, fields, scalars = self._flatten(self.lhs)
+        mask = 0
+        for k, f_ in enumerate(fields):
+            if f_ is e:
+                mask |= 1 << k
+        F = (C.c_void_p * max(1, len(fields)))(*[None if f_ is e else f_.h for f_ in fields])
+        S = (C.c_double * max(1, len(scalars)))(*scalars)
+        self.h = handle(lib().opf_solver_create(target.h, sig.encode(), F, len(fields), S, len(scalars), mask, C.byref(p)), "opf_solver_create")
+        self.lhs_sig = sig
+
+    @staticmethod
+    def _flatten(expr):
+        fields, scalars = [], []
+
+        def rec(x):
+            if isinstance(x, (Field, Unknown)):
+                fields.append(x)
+                return f"F<{len(fields) - 1}>"
+            if isinstance(x, Scalar):
+                scalars.append(float(x.value))
+                return f"S<{len(scalars) - 1}>"
+            parts = [rec(c) for c in x.children]
+            if x.axis is not None:
+                parts.insert(0, str(x.axis))
+            return f"{x.name}<{','.join(parts)}>"
+
+        return rec(_wrap(expr)), fields, scalars
+
+    def levels(self):
+        return lib().opf_solver_levels(self.h)
+
+    def solve(self):
+        """-> EqnSolveState(niter, relerr, abserr)"""
+        sig, fields, scalars = self._flatten(self.rhs)
+        F = (C.c_void_p * max(1, len(fields)))(*[f_.h for f_ in fields])
+        S = (C.c_double * max(1, len(scalars)))(*scalars)
+        st = capi.SolveState()
+        check(lib().opf_solver_solve(self.h, sig.encode(), F, len(fields), S, len(scalars), C.byref(st)))
+        return st
+
+    def __del__(self):
+        try:
+            lib().opf_solver_destroy(self.h)
+        except Exception:
+            pass
