@@ -16,7 +16,7 @@ using namespace opf;
 // ---- examples/FTCS/FTCS.cpp, examples/FTCS2D/FTCS-OMP.cpp:26 and its 3-D extension (BASELINE configs C1, C2)
 OPF_BUILTIN(Add<F<0>, Mul<S<0>, D2C<0, F<1>>>>)
 OPF_BUILTIN(Add<F<0>, Mul<S<0>, Add<D2C<0, F<1>>, D2C<1, F<2>>>>>)
-OPF_BUILTIN(Add<F<0>, Mul<S<0>, Add<Add<D2C<0, F<1>>, D2C<1, F<2>>>, D2C<2, F<3>>>>>)
+// (the 3-D form, BASELINE config C2, lives in builtin_exprs_e.cu)
 // Laplacian (benchmark/Core/LaplaceOp.cpp:80 shape) and the Poisson operator of LidDriven (LidDriven2D.cpp:70)
 OPF_BUILTIN(Add<D2C<0, F<0>>, D2C<1, F<1>>>)
 OPF_BUILTIN(Add<Add<D2C<0, F<0>>, D2C<1, F<1>>>, D2C<2, F<2>>>)

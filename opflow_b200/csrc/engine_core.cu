@@ -299,7 +299,7 @@ namespace opfe {
         return OPF_OK;
     }
     opf::AxisView mesh_axis_view(const opf_mesh_s* m, int d) {
-        opf::AxisView v{nullptr, nullptr, nullptr, nullptr, nullptr};
+        opf::AxisView v{};
         if (d >= m->dim || !m->ax[d].dev) return v;
         const long long st = (long long) m->ax[d].x.size() + 2 * MESH_SLACK;
         const double* base = m->ax[d].dev + MESH_SLACK - m->ext_range.start[d];
@@ -308,6 +308,21 @@ namespace opfe {
         v.rdx = base + 2 * st;
         v.rdxh = base + 3 * st;
         v.rdxc = base + 4 * st;
+        // single-spacing axis: every dx entry bitwise equal -> the reciprocal arrays are constant too (same formulas on the
+        // same inputs; their unset end entries are never read by an in-range stencil)
+        const auto& a = m->ax[d];
+        bool uni = !a.dx.empty();
+        for (size_t i = 1; i < a.dx.size() && uni; ++i) uni = a.dx[i] == a.dx[0];
+        v.uniform = uni ? 1 : 0;
+        if (uni) {
+            const double h = a.dx[0];
+            v.u[opf::CF_X] = 0.0;
+            v.u[opf::CF_DX] = h;
+            v.u[opf::CF_RDX] = 1. / h;
+            v.u[opf::CF_RDXH] = 1. / ((h + h) * 0.5);
+            v.u[opf::CF_RDXC] = 1. / ((((h + h) * 0.5) + ((h + h) * 0.5)) * 0.5);
+            v.u[opf::CF_RDX2] = v.u[opf::CF_RDX] * v.u[opf::CF_RDX];
+        }
         return v;
     }
 }// namespace opfe

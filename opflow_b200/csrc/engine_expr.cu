@@ -598,6 +598,9 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         if (al) li.valign |= 1u << k;
     }
     li.dalign = ((reinterpret_cast<uintptr_t>(li.dst.p + w.start[0]) & 15) == 0) && (dst->pitch1 % 2 == 0) && (dst->pitch2 % 2 == 0);
+    li.uniform = 1;
+    for (int d = 0; d < dst->dim; ++d)
+        if (!a.ax[d].uniform) li.uniform = 0;
     li.tma_ok = dst->dim == 3;
     for (int k = 0; k < p->tree.nfields && li.tma_ok; ++k) {
         const opf_field_s* f = fields[alias0 ? 0 : k];

@@ -38,8 +38,13 @@ namespace opf {
     //   rdx[i]  = 1/dx[i]
     //   rdxh[i] = 1/((dx[i-1]+dx[i])*0.5)
     //   rdxc[i] = 1/((dxl+dxr)*0.5), dxl=(dx[i-1]+dx[i])*0.5, dxr=(dx[i]+dx[i+1])*0.5
+    // `uniform`: every dx entry of the axis is bitwise the same number (MeshBuilder::setMeshOfDim(k, min, max),
+    // CartesianMesh.hpp:292-303, and its symmetric/periodic extension); then u[CF_*] holds that one coefficient and the
+    // kernels read it from the constant bank instead of loading the arrays (u[CF_RDX2] = rdx*rdx).
     struct AxisView {
         const double *x, *dx, *rdx, *rdxh, *rdxc;
+        double u[6];
+        int uniform;
     };
     struct ExprArgs {
         FieldView f[MAX_FIELDS];
@@ -59,6 +64,7 @@ namespace opf {
         int op;   // opf_assign_op
         int mode; // opf_mode
         int alias0;// all field leaves are the same field -> read everything through f[0]
+        int uniform;    // every axis of the mesh has a single spacing (AxisView::uniform): coefficient loads become constants
         unsigned valign;// bit s: rows of field slot s are 16-byte aligned at r.lo[0] (vector loads allowed)
         int dalign;     // same for dst
         int window;     // 0: direct-global skeleton, >0: register-window skeleton allowed
@@ -319,8 +325,9 @@ namespace opf {
         static constexpr int value = N;
     };
     // mesh-coefficient accessors: O is the compile-time offset from the stencil's own index q along its axis
-    enum { CF_X = 0, CF_DX = 1, CF_RDX = 2, CF_RDXH = 3, CF_RDXC = 4 };
+    enum { CF_X = 0, CF_DX = 1, CF_RDX = 2, CF_RDXH = 3, CF_RDXC = 4, CF_RDX2 = 5 };
     struct GAcc {// direct global loads (run-time coordinate evaluator)
+        static constexpr bool uni = false;
         const AxisView& ax;
         int q;
         template <int O> __device__ __forceinline__ double x() const { return __ldg(ax.x + q + O); }
@@ -331,7 +338,9 @@ namespace opf {
     };
     template <class C, int D, int QO>
     struct WAcc {// register-cached coefficients of the window context (hoisted out of the march loop)
+        static constexpr bool uni = C::UNI;
         const C& c;
+        __device__ __forceinline__ double rdx2() const { return c.a.ax[D].u[CF_RDX2]; }
         template <int O> __device__ __forceinline__ double x() const { return c.template coef<D, CF_X, QO + O>(); }
         template <int O> __device__ __forceinline__ double dx() const { return c.template coef<D, CF_DX, QO + O>(); }
         template <int O> __device__ __forceinline__ double rdx() const { return c.template coef<D, CF_RDX, QO + O>(); }
@@ -342,7 +351,10 @@ namespace opf {
     // D2SecondOrderCentered<d>::eval (D2SecondOrderCentered.hpp:161-171)
     template <class P, class Acc>
     __device__ __forceinline__ double d2c_math(double l, double c, double r, bool center, const Acc& m) {
-        if constexpr (P::fast) {
+        if constexpr (P::fast && Acc::uni) {
+            // uniform axis: dx_l == dx_r == dx_c == dx for Corner and Center alike -> one multiply by 1/dx^2
+            return ((r - c) - (c - l)) * m.rdx2();
+        } else if constexpr (P::fast) {
             if (!center) return ((r - c) * m.template rdx<0>() - (c - l) * m.template rdx<-1>()) * m.template rdxh<0>();
             return ((r - c) * m.template rdxh<1>() - (c - l) * m.template rdxh<0>()) * m.template rdxc<0>();
         } else {
@@ -705,6 +717,7 @@ namespace opf {
     template <class E, bool A0, int DIM, int CX>
     struct WinCtx {
         using WI = WinInfo<E, A0, DIM>;
+        static constexpr bool UNI = false;
         const ExprArgs& a;
         int i0, j, k;
         unsigned valign;
@@ -1046,10 +1059,11 @@ namespace opf {
         static constexpr int NS = WI::NS;
     };
 
-    template <class E, bool A0, int CX, int BX, int BY>
+    template <class E, bool A0, int CX, int BX, int BY, bool UNI_>
     struct TmaCtx {
         using G = TmaGeom<E, A0, CX, BX, BY>;
         using WI = typename G::WI;
+        static constexpr bool UNI = UNI_;
         const ExprArgs& a;
         int i0, j, k;
         const double* pl[G::NS][G::NPL];// this thread's centre element (x = i0) in every tapped plane of every slot
@@ -1061,7 +1075,9 @@ namespace opf {
         }
         template <int D, int ARR, int O>
         __device__ __forceinline__ double coef() const {
-            if constexpr (D == 0) return cf0[ARR][O + CR];
+            if constexpr (UNI && ARR != CF_X) return a.ax[D].u[ARR];// constant-bank operand, no load, no register
+            else if constexpr (UNI) return __ldg(a.ax[D].x + ((D == 0 ? i0 : (D == 1 ? j : k)) + O));
+            else if constexpr (D == 0) return cf0[ARR][O + CR];
             else if constexpr (D == 2) return cfm[ARR][O + CR];
             else return cfc[ARR][O + CR];
         }
@@ -1092,17 +1108,26 @@ namespace opf {
                 if (WI::tap(s, di, dj, dk)) return true;
             return false;
         }
+        // FIRST: every tapped row comes from shared memory.  Later march steps: a row (dj, dk) whose successor (dj, dk+1)
+        // was held last step is that successor's registers (the window slides by one plane) -- only rows without a held
+        // successor (the newest plane, and rows tapped in a single plane) are read from shared memory again.
+        template <bool FIRST>
         __device__ __forceinline__ void load_cores() {
             static_for<0, G::NS - 1>([&](auto s) {
-                static_for<WI::ML, WI::MH>([&](auto dk) {
+                static_for<WI::ML, WI::MH>([&](auto dk) {// ascending: [dk+1] still holds last step's values when copied
                     static_for<WI::CL, WI::CH>([&](auto dj) {
                         constexpr int S = decltype(s)::value, DK = decltype(dk)::value, DJ = decltype(dj)::value;
                         if constexpr (row_used(S, DJ, DK)) {
+                            if constexpr (!FIRST && DK < WI::MH && row_used(S, DJ, DK + 1)) {
 #pragma unroll
-                            for (int c = 0; c < CX; c += 2) {
-                                const double2 t = *reinterpret_cast<const double2*>(pl[S][DK - WI::ML] + DJ * G::BW + c);
-                                core[S][DK - WI::ML][DJ + G::HYL][c] = t.x;
-                                core[S][DK - WI::ML][DJ + G::HYL][c + 1] = t.y;
+                                for (int c = 0; c < CX; ++c) core[S][DK - WI::ML][DJ + G::HYL][c] = core[S][DK + 1 - WI::ML][DJ + G::HYL][c];
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CX; c += 2) {
+                                    const double2 t = *reinterpret_cast<const double2*>(pl[S][DK - WI::ML] + DJ * G::BW + c);
+                                    core[S][DK - WI::ML][DJ + G::HYL][c] = t.x;
+                                    core[S][DK - WI::ML][DJ + G::HYL][c + 1] = t.y;
+                                }
                             }
                         }
                     });
@@ -1116,14 +1141,14 @@ namespace opf {
         }
     };
 
-    template <class E, class P, bool A0, int CX, int BX, int BY, int STAGES, bool HASOP>
+    template <class E, class P, bool A0, int CX, int BX, int BY, int STAGES, bool HASOP, bool UNI>
     __global__ void __launch_bounds__(BX* BY) tma_kernel(const __grid_constant__ ExprArgs a,
                                                          const __grid_constant__ TmaMaps<TmaGeom<E, A0, CX, BX, BY>::NS> maps, const DstView dst,
                                                          const double* __restrict__ oldp, const LaunchRange r, const int ch, const int op,
                                                          const int dalign) {
         using G = TmaGeom<E, A0, CX, BX, BY>;
         using WI = typename G::WI;
-        using Ctx = TmaCtx<E, A0, CX, BX, BY>;
+        using Ctx = TmaCtx<E, A0, CX, BX, BY, UNI>;
         constexpr int NS = G::NS, NPL = G::NPL;
         static_assert(STAGES > NPL, "ring must hold the tapped planes plus at least one plane in flight");
         extern __shared__ __align__(128) unsigned char opf_tma_smem[];
@@ -1157,7 +1182,8 @@ namespace opf {
         c.j = y0 + threadIdx.y;
         const bool active = c.i0 < r.hi[0] && c.j < r.hi[1];
         const bool full_tile = c.i0 + CX <= r.hi[0];
-        if (active) c.load_coefs_fixed();
+        if constexpr (!UNI)
+            if (active) c.load_coefs_fixed();
         // byte offset of this thread's centre element inside a tile
         const int toff = ((threadIdx.y + G::HYL) * G::BW + G::HXL + threadIdx.x * CX) * 8;
         // wait for the planes the first step taps except the newest one (waited inside the loop)
@@ -1184,8 +1210,10 @@ namespace opf {
                     for (int s = 0; s < NS; ++s)
                         c.pl[s][q] = reinterpret_cast<const double*>(ring + (size_t) (st * NS + s) * G::TILE_B + toff);
                 }
-                c.load_cores();
-                c.load_coefs_march(m);
+                if (m == m0) c.template load_cores<true>();
+                else
+                    c.template load_cores<false>();
+                if constexpr (!UNI) c.load_coefs_march(m);
                 double out[CX];
                 static_for<0, CX - 1>([&](auto cc) { out[decltype(cc)::value] = E::template ev<0, P, A0, decltype(cc)::value, 0, 0>(c); });
                 const long long o = (long long) c.i0 + (long long) c.j * dst.s1 + (long long) m * dst.s2;
@@ -1346,15 +1374,26 @@ namespace opf {
             kern<<<grid, block, smem, st>>>(a, li.dst, li.old, li.r, ch, li.op, li.valign, li.dalign, pd);
             return (int) cudaGetLastError();
         };
+        (void) stages;// the cp.async staging ring (STAGES > 1) measured no gain over the register prefetch: not instantiated
         if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1>, 1);
-        if (stages >= 6) return go(window_kernel<E, P, A0, DIM, CX, false, 6>, 6);
-        if (stages >= 3) return go(window_kernel<E, P, A0, DIM, CX, false, 4>, 4);
         return go(window_kernel<E, P, A0, DIM, CX, false, 1>, 1);
     }
 
-    template <class E, class P, bool A0, int BY>
+    // tile shape of the TMA skeleton: each thread owns OPF_TMA_CX consecutive cells of a row, a block is (128 / OPF_TMA_CX) x OPF_TMA_BY threads
+#ifndef OPF_TMA_CX
+#define OPF_TMA_CX 2
+#endif
+#ifndef OPF_TMA_BY
+#define OPF_TMA_BY 4
+#endif
+    template <class E, bool A0, int CX, int BY>
+    struct TmaFits {// ring of (planes tapped + 3) tile-plus-halo planes per slot must fit the shared-memory budget
+        using G = TmaGeom<E, A0, CX, 128 / CX, BY>;
+        static constexpr bool value = 128 + (G::NPL + 3) * G::NS * G::TILE_B <= 200 * 1024;
+    };
+    template <class E, class P, bool A0, int BY, int CX>
     int launch_tma(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
-        constexpr int CX = 2, BX = 64;
+        constexpr int BX = 128 / CX;// 128-cell rows: the tile-plus-halo box stays under TMA's 256-element box limit
         using G = TmaGeom<E, A0, CX, BX, BY>;
         constexpr int STAGES = G::NPL + 3;
         static const int ech = getenv("OPF_TCH") ? atoi(getenv("OPF_TCH")) : 0;
@@ -1366,7 +1405,9 @@ namespace opf {
             for (int d = 0; d < 3; ++d) maps.org[s][d] = t.org[d];
         }
         const int n0 = li.r.hi[0] - li.r.lo[0], n1 = li.r.hi[1] - li.r.lo[1], n2 = li.r.hi[2] - li.r.lo[2];
-        const int ch = ech > 0 ? ech : 64;
+        // march chunk per block: short chunks (16 planes) measured best on B200 (513^3: 0.371 ms vs 0.404 ms at 64) -- more,
+        // shorter blocks balance the 148 SMs better than the 2-plane ring prologue costs
+        const int ch = ech > 0 ? ech : 16;
         dim3 block(BX, BY, 1), grid((n0 + BX * CX - 1) / (BX * CX), (n1 + BY - 1) / BY, (n2 + ch - 1) / ch);
         const size_t smem = 128 + (size_t) STAGES * G::NS * G::TILE_B;
         auto go = [&](auto kern) {
@@ -1374,8 +1415,12 @@ namespace opf {
             kern<<<grid, block, smem, st>>>(a, maps, li.dst, li.old, li.r, ch, li.op, li.dalign);
             return (int) cudaGetLastError();
         };
-        if (li.op != 0) return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, true>);
-        return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, false>);
+        if (li.uniform) {
+            if (li.op != 0) return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, true, true>);
+            return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, false, true>);
+        }
+        if (li.op != 0) return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, true, false>);
+        return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, false, false>);
     }
 
     template <class E, class P, bool A0>
@@ -1398,13 +1443,22 @@ namespace opf {
             if constexpr (WinInfo<E, A0, 3>::ok && E::nf > 0) {
                 // TMA tile skeleton: footprint must fit the ring/box budget (<= 200 KB of shared memory)
                 static const int tma_on = getenv("OPF_TMA") ? atoi(getenv("OPF_TMA")) : 1;
-                static const int tby = getenv("OPF_TBY") ? atoi(getenv("OPF_TBY")) : 4;
-                using G4 = TmaGeom<E, A0, 2, 64, 4>;
-                using G8 = TmaGeom<E, A0, 2, 64, 8>;
                 if (tma_on && li.window && li.tma_ok && (li.r.hi[0] - li.r.lo[0]) >= 64) {
-                    if constexpr (128 + (G8::NPL + 3) * G8::NS * G8::TILE_B <= 200 * 1024)
-                        if (tby == 8) return launch_tma<E, P, A0, 8>(a, li, st);
-                    if constexpr (128 + (G4::NPL + 3) * G4::NS * G4::TILE_B <= 200 * 1024) return launch_tma<E, P, A0, 4>(a, li, st);
+#ifdef OPF_TMA_SWEEP
+                    // tuning build: tile shape selectable at run time (OPF_TBY in {4,8}, OPF_TCX in {2,4})
+                    static const int tby = getenv("OPF_TBY") ? atoi(getenv("OPF_TBY")) : OPF_TMA_BY;
+                    static const int tcx = getenv("OPF_TCX") ? atoi(getenv("OPF_TCX")) : OPF_TMA_CX;
+                    if constexpr (TmaFits<E, A0, 4, 8>::value)
+                        if (tby == 8 && tcx == 4) return launch_tma<E, P, A0, 8, 4>(a, li, st);
+                    if constexpr (TmaFits<E, A0, 2, 8>::value)
+                        if (tby == 8 && tcx == 2) return launch_tma<E, P, A0, 8, 2>(a, li, st);
+                    if constexpr (TmaFits<E, A0, 4, 4>::value)
+                        if (tby == 4 && tcx == 4) return launch_tma<E, P, A0, 4, 4>(a, li, st);
+                    if constexpr (TmaFits<E, A0, 2, 4>::value)
+                        if (tby == 4 && tcx == 2) return launch_tma<E, P, A0, 4, 2>(a, li, st);
+#endif
+                    if constexpr (TmaFits<E, A0, OPF_TMA_CX, OPF_TMA_BY>::value) return launch_tma<E, P, A0, OPF_TMA_BY, OPF_TMA_CX>(a, li, st);
+                    else if constexpr (TmaFits<E, A0, 2, 4>::value) return launch_tma<E, P, A0, 4, 2>(a, li, st);
                 }
                 if (li.window) return launch_window<E, P, A0, 3>(a, li, st);
             }
