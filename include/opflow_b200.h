@@ -118,6 +118,9 @@ typedef struct {
 /* ExprBuilder<CartesianField>::build (CartesianField.hpp:929-938): calculateRanges :950-1029, validateRanges
  * :941-948, storage = localRange inflated by padding, updatePadding(). */
 opf_field_t opf_field_create(const opf_field_desc* desc, const char* name);
+/* the host half of build(): ranges, split and neighbour lists of a description WITHOUT device storage (works with no GPU; the
+ * handle answers opf_field_get_range / get_loc / padding / neighbors / destroy, every compute entry point rejects it). */
+opf_field_t opf_field_plan(const opf_field_desc* desc, const char* name);
 opf_field_t opf_field_clone(opf_field_t f, const char* name); /* CartesianField copy ctor :57-68 (deep copy) */
 int opf_field_destroy(opf_field_t f);
 int opf_field_dim(opf_field_t f);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "opf_mesh_get_axis": (C.c_int, [_V, C.c_int, _D, _D, _D, C.c_int]),
     "opf_mesh_destroy": (C.c_int, [_V]),
     "opf_field_create": (_V, [C.POINTER(FieldDesc), C.c_char_p]),
+    "opf_field_plan": (_V, [C.POINTER(FieldDesc), C.c_char_p]),
     "opf_field_clone": (_V, [_V, C.c_char_p]),
     "opf_field_destroy": (C.c_int, [_V]),
     "opf_field_dim": (C.c_int, [_V]),

@@ -92,7 +92,7 @@ namespace {
 namespace opfe {
     bool comm_active() { return nc().comm != nullptr; }
 
-    int halo_exchange(opf_field_s* f) {
+    int halo_exchange(opf_field_s* f, cudaStream_t st) {
         Nccl& n = nc();
         if (f->neighbors.empty()) return OPF_OK;
         if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
@@ -124,7 +124,7 @@ namespace opfe {
         for (int i = 0; i < nn; ++i) {
             const long long cnt = soff[i + 1] - soff[i];
             const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
-            box_copy_kernel<<<blocks, 256, 0, c.stream>>>(fb, f->pitch1, f->pitch2, f->halo_send + soff[i], lr(f->neighbors[i].send), 1);
+            box_copy_kernel<<<blocks, 256, 0, st>>>(fb, f->pitch1, f->pitch2, f->halo_send + soff[i], lr(f->neighbors[i].send), 1);
             c.launches++;
         }
         OPF_CUDA(cudaGetLastError());
@@ -139,19 +139,19 @@ namespace opfe {
         OPF_NCCL(n.GroupStart());
         for (int k = 0; k < nn; ++k) {
             const int i = sorder[k];
-            OPF_NCCL(n.Send(f->halo_send + soff[i], (size_t) (soff[i + 1] - soff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, c.stream));
+            OPF_NCCL(n.Send(f->halo_send + soff[i], (size_t) (soff[i + 1] - soff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, st));
         }
         for (int k = 0; k < nn; ++k) {
             const int i = rorder[k];
             if (roff[i + 1] - roff[i] > 0)
-                OPF_NCCL(n.Recv(f->halo_recv + roff[i], (size_t) (roff[i + 1] - roff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, c.stream));
+                OPF_NCCL(n.Recv(f->halo_recv + roff[i], (size_t) (roff[i + 1] - roff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, st));
         }
         OPF_NCCL(n.GroupEnd());
         for (int i = 0; i < nn; ++i) {
             const long long cnt = roff[i + 1] - roff[i];
             if (cnt <= 0) continue;
             const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
-            box_copy_kernel<<<blocks, 256, 0, c.stream>>>(fb, f->pitch1, f->pitch2, f->halo_recv + roff[i], lr(f->neighbors[i].recv), 0);
+            box_copy_kernel<<<blocks, 256, 0, st>>>(fb, f->pitch1, f->pitch2, f->halo_recv + roff[i], lr(f->neighbors[i].recv), 0);
             c.launches++;
         }
         OPF_CUDA(cudaGetLastError());

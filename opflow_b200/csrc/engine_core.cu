@@ -63,7 +63,11 @@ int opf_init(int device) {
     OPF_CUDA(cudaSetDevice(device));
     c.device = device;
     OPF_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    OPF_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+    {// halo pack / NCCL / unpack must not queue behind the interior sweep's blocks: highest priority
+        int least = 0, greatest = 0;
+        OPF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        OPF_CUDA(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, greatest));
+    }
     OPF_CUDA(cudaEventCreate(&c.ev0));
     OPF_CUDA(cudaEventCreate(&c.ev1));
     OPF_CUDA(cudaEventCreateWithFlags(&c.ev_comm, cudaEventDisableTiming));
@@ -465,14 +469,16 @@ namespace opfe {
         return true;
     }
     // launches ops[b, e) as ONE kernel
-    static int launch_fill_group(opf_field_s* f, const std::vector<FillOp>& ops, size_t b, size_t e, int lww) {
+    static int launch_fill_group(opf_field_s* f, const std::vector<FillOp>& ops, size_t b, size_t e, int lww, const Range* clip = nullptr) {
         MultiFill mf;
         mf.n = 0;
         mf.lww = lww;
         mf.start[0] = 0;
         for (size_t i = b; i < e && mf.n < 6; ++i) {
-            if (!make_fill_params(f, ops[i], mf.op[mf.n])) continue;
-            mf.start[mf.n + 1] = mf.start[mf.n] + ops[i].r.count();
+            FillOp op = ops[i];
+            if (clip) op.r = common(op.r, *clip);
+            if (!make_fill_params(f, op, mf.op[mf.n])) continue;
+            mf.start[mf.n + 1] = mf.start[mf.n] + op.r.count();
             mf.n++;
         }
         if (mf.n == 0) return OPF_OK;
@@ -588,17 +594,24 @@ namespace opfe {
         clip(f->fill2);
     }
 
-    int field_update_padding(opf_field_s* f) {
+    // steps 0 and 1 of updatePadding (physical boundaries), optionally restricted to a box
+    int field_fill_bc(opf_field_s* f, const Range* clip) {
         // step 0: all Corner-Dirichlet boundary faces in one launch (pure writes, last writer wins on shared edges)
         if (!f->fill0.empty())
-            if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1)) return rc;
+            if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1, clip)) return rc;
         // step 1: one launch per axis (its two sides are independent; later axes read earlier axes' ghosts)
         for (size_t i = 0; i < f->fill1.size();) {
             size_t e = i + 1;
             while (e < f->fill1.size() && f->fill1[e].axis == f->fill1[i].axis) ++e;
-            if (int rc = launch_fill_group(f, f->fill1, i, e, 0)) return rc;
+            if (int rc = launch_fill_group(f, f->fill1, i, e, 0, clip)) return rc;
             i = e;
         }
+        return OPF_OK;
+    }
+
+    int field_update_padding(opf_field_s* f) {
+        if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
+        if (int rc = field_fill_bc(f, nullptr)) return rc;
         if (f->split_map.size() <= 1) {
             // step 2: periodic copies, one launch per axis
             for (size_t i = 0; i < f->fill2.size();) {
@@ -608,7 +621,7 @@ namespace opfe {
                 i = e;
             }
         } else {
-            if (int rc = halo_exchange(f)) return rc;
+            if (int rc = halo_exchange(f, ctx().stream)) return rc;
         }
         return OPF_OK;
     }
@@ -643,8 +656,15 @@ namespace opfe {
         for (int i = 0; i < (int) f->split_map.size(); ++i) {
             for (int k = 0; k < range_count; ++k) {
                 Range r = f->split_map[i];
+                // digit q of k (0 none, 1 +period, 2 -period) belongs to the q-th PERIODIC axis.  The reference applies digit d
+                // to axis d (CartesianField.hpp:316-317), which is the same thing whenever the periodic axes are the leading
+                // ones (every reference program: fully periodic boxes) and shifts along a non-periodic axis otherwise -- a
+                // defect not reproduced here.
+                int q = 0;
                 for (int d = 0; d < dim; ++d) {
-                    const int direction = (k % ipow3(d + 1)) / ipow3(d);
+                    if (!periodic[d]) continue;
+                    const int direction = (k % ipow3(q + 1)) / ipow3(q);
+                    ++q;
                     if (direction == 2) {
                         r.start[d] -= ext[d] - 1;
                         r.end[d] -= ext[d] - 1;
@@ -666,14 +686,18 @@ namespace opfe {
 // ============================================================================================== field
 extern "C" {
 
-opf_field_t opf_field_create(const opf_field_desc* desc, const char* name) {
+// host part of ExprBuilder::build: ranges, decomposition, neighbours, storage geometry -- no device needed
+static opf_field_s* plan_field(const opf_field_desc* desc, const char* name, bool with_device) {
     if (!desc || !desc->mesh) {
         fail(OPF_ERR_INVALID, "opf_field_create: null desc/mesh");
         return nullptr;
     }
-    if (require_device()) return nullptr;
     opf_mesh_s* m = desc->mesh;
-    if (mesh_upload(m)) return nullptr;
+    for (int d = 0; d < m->dim; ++d)
+        if (!m->ax[d].set) {
+            fail(OPF_ERR_INVALID, "mesh axis %d has no coordinates (setMeshOfDim missing)", d);
+            return nullptr;
+        }
     auto* f = new opf_field_s();
     f->name = name ? name : "";
     f->dim = m->dim;
@@ -691,6 +715,7 @@ opf_field_t opf_field_create(const opf_field_desc* desc, const char* name) {
                 bc.face_range = from_c(desc->bc[d][s].face_range, dim);
                 const long long n = bc.face_range.count();
                 bc.face.assign(desc->bc[d][s].face, desc->bc[d][s].face + n);
+                if (!with_device) continue;
                 if (cudaMalloc(&bc.face_dev, sizeof(double) * n) != cudaSuccess
                     || cudaMemcpy(bc.face_dev, bc.face.data(), sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
                     fail(OPF_ERR_CUDA, "BC face upload failed");
@@ -772,6 +797,22 @@ opf_field_t opf_field_create(const opf_field_desc* desc, const char* name) {
     f->pitch1 = dim >= 2 ? ((f->lead + e0 + 15) / 16) * 16 : 0;
     f->pitch2 = dim >= 3 ? f->pitch1 * e1 : 0;
     f->elems = dim == 1 ? f->lead + e0 + 16 : (dim == 2 ? f->pitch1 * e1 : f->pitch2 * e2) + 16;
+    return f;
+}
+
+// ranges / split / neighbour queries of a field description without touching a device (host logic only; used by the
+// CPU-side decomposition tests).  The handle supports opf_field_get_range / get_loc / padding / neighbors / destroy.
+opf_field_t opf_field_plan(const opf_field_desc* desc, const char* name) { return plan_field(desc, name, false); }
+
+opf_field_t opf_field_create(const opf_field_desc* desc, const char* name) {
+    if (!desc || !desc->mesh) {
+        fail(OPF_ERR_INVALID, "opf_field_create: null desc/mesh");
+        return nullptr;
+    }
+    if (require_device()) return nullptr;
+    if (mesh_upload(desc->mesh)) return nullptr;
+    opf_field_s* f = plan_field(desc, name, true);
+    if (!f) return nullptr;
     if (cudaMalloc(&f->buf[0], sizeof(double) * f->elems) != cudaSuccess) {
         fail(OPF_ERR_CUDA, "cudaMalloc of %lld doubles failed for field '%s'", f->elems, f->name.c_str());
         cudaGetLastError();
@@ -865,6 +906,7 @@ int opf_field_device_ptr(opf_field_t f, double** first, long long* pitch1, long 
 }
 
 static int copy_box(opf_field_s* f, const Range& r, double* host, bool to_device) {
+    if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
     if (!common(r, f->storage).covers(r) || r.count() <= 0) return fail(OPF_ERR_RANGE, "transfer range outside the storage of field '%s'", f->name.c_str());
     const size_t n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
     double* dev = f->biased(f->cur) + ((long long) r.start[0] + (long long) r.start[1] * f->pitch1 + (long long) r.start[2] * f->pitch2);

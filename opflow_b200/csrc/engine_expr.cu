@@ -408,6 +408,7 @@ namespace opfe {
         for (int k = 0; k < t.nfields; ++k) {
             const opf_field_s* f = fields[k];
             if (!f) return fail(OPF_ERR_INVALID, "field argument %d is null", k);
+            if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
             a.f[k].p = f->biased(f->cur);
             a.f[k].s1 = f->pitch1;
             a.f[k].s2 = f->pitch2;
@@ -457,6 +458,52 @@ namespace opfe {
                         return fail(OPF_ERR_RANGE, "expression '%s' reads mesh spacings outside the mesh's extended range on axis %d", p.sig.c_str(), d);
         }
         return OPF_OK;
+    }
+}// namespace opfe
+
+namespace opfe {
+    // Decomposition of an assignment over a field whose neighbours all lie along ONE axis (slab decomposition):
+    // the planes a neighbour needs (within `padding` of the shared face) are swept first so that their exchange runs under
+    // the interior sweep.
+    struct SlabPlan {
+        int axis = -1;
+        bool has_lo = false, has_hi = false;
+        Range lo, hi, mid;               // sub-boxes of the written range w
+        Range clip_lo, clip_hi, clip_mid;// storage sub-boxes for the matching BC fills
+    };
+    static bool slab_plan(const opf_field_s* f, const Range& w, SlabPlan& sp) {
+        if (f->neighbors.empty() || w.count() <= 0 || f->padding <= 0) return false;
+        for (const auto& nb : f->neighbors) {
+            int partial = -1, npartial = 0;
+            for (int d = 0; d < f->dim; ++d)
+                if (!(nb.send.start[d] == f->local.start[d] && nb.send.end[d] == f->local.end[d])) {
+                    partial = d;
+                    ++npartial;
+                }
+            if (npartial != 1) return false;// whole-block or edge/corner neighbour: not a slab layout
+            if (sp.axis >= 0 && sp.axis != partial) return false;
+            sp.axis = partial;
+            if (nb.send.start[partial] == f->local.start[partial]) sp.has_lo = true;
+            else if (nb.send.end[partial] == f->local.end[partial])
+                sp.has_hi = true;
+            else
+                return false;
+        }
+        const int ax = sp.axis, pad = f->padding;
+        if (f->local.end[ax] - f->local.start[ax] < 2 * pad + 1) return false;// slab too thin to have an interior
+        sp.lo = sp.hi = sp.mid = w;
+        const int lo_end = sp.has_lo ? std::min(w.end[ax], std::max(w.start[ax], f->local.start[ax] + pad)) : w.start[ax];
+        const int hi_start = sp.has_hi ? std::max(lo_end, std::min(w.end[ax], f->local.end[ax] - pad)) : w.end[ax];
+        sp.lo.end[ax] = lo_end;
+        sp.hi.start[ax] = hi_start;
+        sp.mid.start[ax] = lo_end;
+        sp.mid.end[ax] = hi_start;
+        sp.clip_lo = sp.clip_hi = sp.clip_mid = f->storage;
+        sp.clip_lo.end[ax] = lo_end;
+        sp.clip_hi.start[ax] = hi_start;
+        if (sp.has_lo) sp.clip_mid.start[ax] = lo_end;
+        if (sp.has_hi) sp.clip_mid.end[ax] = hi_start;
+        return true;
     }
 }// namespace opfe
 
@@ -555,6 +602,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     if (!dst || !signature) return fail(OPF_ERR_INVALID, "null argument");
     if (op < 0 || op > 4) return fail(OPF_ERR_UNSUPPORTED, "assign op %d is integer-only in the reference (Mod/And/Or/Xor/Shift)", op);
     if (int rc = require_device()) return rc;
+    if (!dst->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", dst->name.c_str());
     Plan* p;
     if (int rc = get_plan(signature, &p, true)) return rc;
     const Range w = common(dst->assignable, dst->local);// FieldAssigner.hpp:49
@@ -616,11 +664,43 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         t.org[2] = f->storage.start[2];
         if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.stride_b[0] & 15) || (t.stride_b[1] & 15) || f->dim != 3) li.tma_ok = 0;
     }
-    if (w.count() > 0) {
-        const int rc = p->fn(&a, &li, ctx().stream);
-        if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have");
+    auto launch_box = [&](const Range& box) -> int {
+        if (box.count() <= 0) return OPF_OK;
+        opf::LaunchInfo lb = li;
+        for (int d = 0; d < 3; ++d) {
+            lb.r.lo[d] = box.start[d];
+            lb.r.hi[d] = box.end[d];
+        }
+        const int rc = p->fn(&a, &lb, ctx().stream);
+        if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have, or its TMA descriptor could not be encoded");
         ctx().launches++;
+        return OPF_OK;
+    };
+    // ---- slab-decomposed destination: halo exchange overlapped with the interior sweep (replaces the serial
+    // pack -> MPI_Isend/Irecv -> Waitall -> unpack of CartesianField.hpp:630-768).  Order:
+    //   compute stream: boundary-slab sweeps, BC fill of those planes | interior sweep, BC fill of the rest | wait(comm)
+    //   comm stream   :                         wait(boundary) pack -> NCCL send/recv -> unpack
+    SlabPlan sp;
+    static const int overlap_on = getenv("OPF_OVERLAP") ? atoi(getenv("OPF_OVERLAP")) : 1;
+    if (overlap_on && !(flags & OPF_ASSIGN_NO_PADDING) && comm_active() && slab_plan(dst, w, sp)) {
+        Context& c = ctx();
+        if (int rc = launch_box(sp.lo)) return rc;
+        if (int rc = launch_box(sp.hi)) return rc;
+        if (use_twin) dst->cur = wr;
+        if (sp.has_lo)
+            if (int rc = field_fill_bc(dst, &sp.clip_lo)) return rc;
+        if (sp.has_hi)
+            if (int rc = field_fill_bc(dst, &sp.clip_hi)) return rc;
+        OPF_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+        OPF_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_compute, 0));
+        if (int rc = halo_exchange(dst, c.comm_stream)) return rc;
+        OPF_CUDA(cudaEventRecord(c.ev_comm, c.comm_stream));
+        if (int rc = launch_box(sp.mid)) return rc;
+        if (int rc = field_fill_bc(dst, &sp.clip_mid)) return rc;
+        OPF_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
+        return OPF_OK;
     }
+    if (int rc = launch_box(w)) return rc;
     if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep
     if (flags & OPF_ASSIGN_NO_PADDING) return OPF_OK;
     return field_update_padding(dst);// CartesianField.hpp:231

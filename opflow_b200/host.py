@@ -387,7 +387,7 @@ class ExprBuilder:
         self.split = (n_ranks, rank, split_map)
         return self
 
-    def build(self):
+    def build(self, plan_only=False):
         d = capi.FieldDesc()
         d.mesh = self.mesh.h
         dim = self.mesh.dim
@@ -411,8 +411,12 @@ class ExprBuilder:
             d.n_ranks, d.rank, d.split_map = n, r, arr
         else:
             d.n_ranks, d.rank, d.split_map = 0, 0, None
-        h = handle(lib().opf_field_create(C.byref(d), self.name.encode()), "opf_field_create")
+        h = handle((lib().opf_field_plan if plan_only else lib().opf_field_create)(C.byref(d), self.name.encode()), "opf_field_create")
         return Field(h, self.mesh, self.name)
+
+    def plan(self):
+        """ranges / split / neighbour lists only (opf_field_plan): no device storage, works without a GPU"""
+        return self.build(plan_only=True)
 
 
 def split_even(mesh: CartesianMesh, n_ranks):
