@@ -163,6 +163,10 @@ struct opf_field_s {
     int cur = 0;
     long long pitch1 = 0, pitch2 = 0, lead = 0, elems = 0;
     std::vector<opfe::FillOp> fill0, fill1, fill2;// step 0, step 1, step 2 (single-rank periodic)
+    // step 0 writes time-independent values (ConstDircBC / pre-evaluated FunctorDircBC) into Corner boundary nodes that no
+    // assignment kernel ever touches (they lie outside assignableRange): once a buffer holds them they stay valid until
+    // someone writes the buffer from outside (upload, swap, BC change), so the launch is skipped while this flag is set.
+    bool bc0_clean[2] = {false, false};
     // halo staging (multi-rank)
     double* halo_send = nullptr;
     double* halo_recv = nullptr;

@@ -597,8 +597,10 @@ namespace opfe {
     // steps 0 and 1 of updatePadding (physical boundaries), optionally restricted to a box
     int field_fill_bc(opf_field_s* f, const Range* clip) {
         // step 0: all Corner-Dirichlet boundary faces in one launch (pure writes, last writer wins on shared edges)
-        if (!f->fill0.empty())
+        if (!f->fill0.empty() && !f->bc0_clean[f->cur]) {
             if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1, clip)) return rc;
+            if (!clip) f->bc0_clean[f->cur] = true;// a clipped caller marks the buffer itself once all its boxes are done
+        }
         // step 1: one launch per axis (its two sides are independent; later axes read earlier axes' ghosts)
         for (size_t i = 0; i < f->fill1.size();) {
             size_t e = i + 1;
@@ -630,6 +632,7 @@ namespace opfe {
         if (f->buf[1 - f->cur]) return OPF_OK;
         OPF_CUDA(cudaMalloc(&f->buf[1 - f->cur], sizeof(double) * f->elems));
         OPF_CUDA(cudaMemcpyAsync(f->buf[1 - f->cur], f->buf[f->cur], sizeof(double) * f->elems, cudaMemcpyDeviceToDevice, ctx().stream));
+        f->bc0_clean[1 - f->cur] = f->bc0_clean[f->cur];
         return OPF_OK;
     }
 
@@ -837,6 +840,8 @@ opf_field_t opf_field_clone(opf_field_t src, const char* name) {
     f->name = name ? name : src->name;
     f->mesh->refcount++;
     f->buf[0] = f->buf[1] = nullptr;
+    f->bc0_clean[0] = src->bc0_clean[src->cur];
+    f->bc0_clean[1] = false;
     f->cur = 0;
     f->halo_send = f->halo_recv = nullptr;
     f->halo_elems = 0;
@@ -907,6 +912,7 @@ int opf_field_device_ptr(opf_field_t f, double** first, long long* pitch1, long 
 
 static int copy_box(opf_field_s* f, const Range& r, double* host, bool to_device) {
     if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
+    if (to_device) f->bc0_clean[f->cur] = false;
     if (!common(r, f->storage).covers(r) || r.count() <= 0) return fail(OPF_ERR_RANGE, "transfer range outside the storage of field '%s'", f->name.c_str());
     const size_t n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
     double* dev = f->biased(f->cur) + ((long long) r.start[0] + (long long) r.start[1] * f->pitch1 + (long long) r.start[2] * f->pitch2);
@@ -962,6 +968,7 @@ int opf_field_update_padding(opf_field_t f) {
 int opf_field_set_bc_value(opf_field_t f, int axis, int pos, double value) {
     if (!f || axis < 0 || axis >= f->dim || pos < 0 || pos > 1) return fail(OPF_ERR_INVALID, "bad argument");
     f->bc[axis][pos].value = value;
+    f->bc0_clean[0] = f->bc0_clean[1] = false;
     return OPF_OK;
 }
 
@@ -970,6 +977,7 @@ int opf_field_swap(opf_field_t a, opf_field_t b) {
     if (a->elems != b->elems || a->pitch1 != b->pitch1 || a->pitch2 != b->pitch2 || a->lead != b->lead)
         return fail(OPF_ERR_INVALID, "swap of fields with different storage shapes");
     std::swap(a->buf[a->cur], b->buf[b->cur]);
+    a->bc0_clean[a->cur] = b->bc0_clean[b->cur] = false;
     return OPF_OK;
 }
 

@@ -697,6 +697,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         OPF_CUDA(cudaEventRecord(c.ev_comm, c.comm_stream));
         if (int rc = launch_box(sp.mid)) return rc;
         if (int rc = field_fill_bc(dst, &sp.clip_mid)) return rc;
+        dst->bc0_clean[dst->cur] = true;
         OPF_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
         return OPF_OK;
     }

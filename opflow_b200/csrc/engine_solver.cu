@@ -250,6 +250,7 @@ namespace {
                 }
             }
         cudaMemsetAsync(c->buf[0], 0, sizeof(double) * c->elems, ctx().stream);
+        c->bc0_clean[0] = c->bc0_clean[1] = false;
         return c;
     }
 
