@@ -57,7 +57,7 @@ typedef enum { OPF_MESHEXT_UNDEFINED = 0, OPF_MESHEXT_SYMM = 1, OPF_MESHEXT_PERI
 typedef enum { OPF_MODE_EXACT = 0, OPF_MODE_FAST = 1 } opf_mode;
 typedef enum { OPF_RED_SUM = 0, OPF_RED_MAX = 1, OPF_RED_MIN = 2, OPF_RED_ABSMAX = 3, OPF_RED_SUMSQ = 4 } opf_reduce_op;
 
-typedef struct { int start[OPF_MAX_DIM], end[OPF_MAX_DIM]; } opf_range;
+typedef struct opf_range { int start[OPF_MAX_DIM], end[OPF_MAX_DIM]; } opf_range;
 
 typedef struct opf_mesh_s* opf_mesh_t;
 typedef struct opf_field_s* opf_field_t;
@@ -93,7 +93,7 @@ int opf_mesh_get_axis(opf_mesh_t m, int axis, double* x, double* dx, double* idx
 int opf_mesh_destroy(opf_mesh_t m);
 
 /* ------------------------------------------------------------------------------------------------ field */
-typedef struct {
+typedef struct opf_bc_desc {
     int type;            /* opf_bctype */
     double value;        /* ConstDircBC / ConstNeumBC value (DircBC.hpp:40-50) */
     const double* face;  /* FunctorDircBC / FunctorNeumBC pre-evaluated on the host (DircBC.hpp:83-118): one value per
@@ -101,7 +101,7 @@ typedef struct {
     opf_range face_range;
 } opf_bc_desc;
 
-typedef struct {
+typedef struct opf_field_desc {
     opf_mesh_t mesh;
     int loc[OPF_MAX_DIM];                 /* opf_loc per axis  (ExprBuilder::setLoc, CartesianField.hpp:811-824) */
     opf_bc_desc bc[OPF_MAX_DIM][2];       /* [axis][opf_dimpos] (setBC :827-895) */
@@ -207,7 +207,7 @@ typedef enum { OPF_SOLVER_NONE = 0, OPF_SOLVER_JACOBI = 1, OPF_SOLVER_SMG = 2, O
                OPF_SOLVER_PCG = 5, OPF_SOLVER_GMRES = 6, OPF_SOLVER_FGMRES = 7, OPF_SOLVER_LGMRES = 8,
                OPF_SOLVER_BICGSTAB = 9 } opf_solver_type;
 
-typedef struct {            /* StructSolverParamsBase :39-51 + the per-solver fields the engine honours */
+typedef struct opf_solver_params { /* StructSolverParamsBase :39-51 + the per-solver fields the engine honours */
     int type, precond;      /* opf_solver_type */
     double tol;             /* relative residual ||r||2/||b||2 */
     int max_iter;
@@ -218,7 +218,7 @@ typedef struct {            /* StructSolverParamsBase :39-51 + the per-solver fi
     int print_level;
 } opf_solver_params;
 
-typedef struct { int niter; double relerr, abserr; } opf_solve_state; /* EqnSolveState EqnSolveHandler.hpp:17-25 */
+typedef struct opf_solve_state { int niter; double relerr, abserr; } opf_solve_state; /* EqnSolveState EqnSolveHandler.hpp:17-25 */
 
 /* makeEqnSolveHandler(f, target, solver) -> HYPREEqnSolveHandler ctor + init() (HYPREEqnSolveHandler.hpp:44-117), matrix-free:
  * the equation  lhs(e) == rhs  is given as two expression signatures.  `lhs` must be linear in the unknown e; the leaves of
@@ -234,6 +234,9 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
  * and refreshes its padding (returnValues :181-188).  Initial guess = current target values (initx :119-123). */
 int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_t* rhs_fields, int n_rhs_fields,
                      const double* rhs_scalars, int n_rhs_scalars, opf_solve_state* state);
+/* refresh the non-unknown leaves of lhs (coefficient fields, scalars such as dt) before the next solve: the handler's equation
+ * lambda captures them by reference and is re-evaluated on every solve() (HYPREEqnSolveHandler.hpp:190-209 -> generateAb). */
+int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_fields, const double* lhs_scalars, int n_lhs_scalars);
 int opf_solver_levels(opf_solver_t s); /* number of multigrid levels built (1 = no hierarchy) */
 int opf_solver_destroy(opf_solver_t s);
 

@@ -124,6 +124,7 @@ SIGNATURES = {
     "opf_assign_ex": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int]),
     "opf_solver_create": (_V, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_uint, C.POINTER(SolverParams)]),
     "opf_solver_solve": (C.c_int, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.POINTER(SolveState)]),
+    "opf_solver_update": (C.c_int, [_V, C.POINTER(_V), C.c_int, _D, C.c_int]),
     "opf_solver_levels": (C.c_int, [_V]),
     "opf_solver_destroy": (C.c_int, [_V]),
     "opf_reduce": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, _R, _D]),

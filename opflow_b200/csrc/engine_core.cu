@@ -78,6 +78,11 @@ int opf_init(int device) {
     c.red_cap = 4 * c.sm_count * 4 + 8;
     OPF_CUDA(cudaMalloc(&c.red_buf, sizeof(double) * c.red_cap));
     OPF_CUDA(cudaMallocHost(&c.red_host, sizeof(double) * 8));
+    if (const char* m = getenv("OPF_MODE")) {// lets an unchanged user program run bit-exactly: OPF_MODE=exact
+        if (!strcmp(m, "exact") || !strcmp(m, "EXACT") || !strcmp(m, "0")) c.mode = OPF_MODE_EXACT;
+        else if (!strcmp(m, "fast") || !strcmp(m, "FAST") || !strcmp(m, "1"))
+            c.mode = OPF_MODE_FAST;
+    }
     c.inited = true;
     return OPF_OK;
 }

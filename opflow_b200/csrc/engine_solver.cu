@@ -226,6 +226,10 @@ struct opf_solver_s {
     std::vector<Level> lv;
     opf_field_s *X = nullptr, *B = nullptr, *R = nullptr, *P = nullptr, *Z = nullptr, *Q = nullptr;
     opf_field_s *R0 = nullptr, *V = nullptr, *S = nullptr, *T = nullptr, *E0 = nullptr;// BiCGSTAB extras, boundary-data field
+    // an `lhs` that also carries terms without the unknown (the front-end passes  lhs(e) - rhs(e)  when both sides of `==`
+    // contain e) is affine: lhs(p) = A.p + c.  C0 = lhs(0 with homogeneous BCs) = c is removed from every operator application.
+    opf_field_s* C0 = nullptr;
+    bool affine = false;
     bool pinned = false;
     long long pin_off = 0;
     bool setup_done = false, mg = false, has_res_sig = false;
@@ -270,6 +274,8 @@ namespace {
         for (int k = 0; k < nf; ++k) F[k] = ((s->mask >> k) & 1u) ? in : s->lhs_fields[k];
         if (int rc = opf_assign_ex(out, OPF_OP_EQ, s->lhs_sig.c_str(), F, nf, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING))
             return rc;
+        if (s->affine && level == 0)
+            if (int rc = assign(out, "Sub<F<0>,F<1>>", {out, s->C0}, {})) return rc;
         if (s->pin_active && pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
             copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(out->biased(out->cur), in->biased(in->cur), s->lv[level].pin_off);
             ctx().launches++;
@@ -278,7 +284,7 @@ namespace {
     }
     // r = b - lhs(x)
     int residual(Solver* s, opf_field_s* x, opf_field_s* b, opf_field_s* r, opf_field_s* scratch, int level, bool pin = true) {
-        if (s->has_res_sig && !(s->pin_active && pin)) {
+        if (s->has_res_sig && !(s->pin_active && pin) && !s->affine) {
             if (int rc = field_update_padding(x)) return rc;
             opf_field_t F[OPF_MAX_FIELDS];
             const int nf = (int) s->lhs_fields.size();
@@ -586,10 +592,29 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
 
 int opf_solver_levels(opf_solver_t s) { return s ? (int) s->lv.size() : -1; }
 
+int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_fields, const double* lhs_scalars, int n_lhs_scalars) {
+    if (!s) return fail(OPF_ERR_INVALID, "null solver");
+    if (n_lhs_fields != (int) s->lhs_fields.size() || n_lhs_scalars != (int) s->lhs_scalars.size())
+        return fail(OPF_ERR_INVALID, "opf_solver_update: leaf counts differ from opf_solver_create (%d/%d fields, %d/%d scalars)", n_lhs_fields,
+                    (int) s->lhs_fields.size(), n_lhs_scalars, (int) s->lhs_scalars.size());
+    bool changed = false;
+    for (int k = 0; k < n_lhs_fields; ++k) {
+        opf_field_s* f = ((s->mask >> k) & 1u) ? nullptr : lhs_fields[k];
+        if (f != s->lhs_fields[k]) changed = true;
+        s->lhs_fields[k] = f;
+    }
+    for (int k = 0; k < n_lhs_scalars; ++k) {
+        if (lhs_scalars[k] != s->lhs_scalars[k]) changed = true;
+        s->lhs_scalars[k] = lhs_scalars[k];
+    }
+    if (changed) s->setup_done = false;// a static operator with new coefficients is set up again
+    return OPF_OK;
+}
+
 int opf_solver_destroy(opf_solver_t s) {
     if (!s) return OPF_OK;
     for (auto& L : s->lv) free_level_fields(L);
-    for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0})
+    for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0, s->C0})
         if (f) opf_field_destroy(f);
     delete s;
     return OPF_OK;
@@ -698,6 +723,22 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     // ---- setup (once when static_mat, else every solve -- the reference re-creates the HYPRE solver every time)
     if (!s->setup_done || !s->params.static_mat) {
         s->pin_active = false;
+        {// constant part of an affine lhs (multigrid levels only exist for pure operators, which have none)
+            s->affine = false;
+            bool pure = true;
+            for (size_t k = 0; k < s->lhs_fields.size(); ++k)
+                if (!((s->mask >> k) & 1u)) pure = false;
+            if (!pure || !s->lhs_scalars.empty()) {
+                if (!s->C0 && !(s->C0 = clone_homogeneous(t, "kry.c0"))) return OPF_ERR_CUDA;
+                if (int rc = assign(s->Z, "S<0>", {}, {0.0})) return rc;
+                if (int rc = apply_lhs(s, s->Z, s->C0, 0, false)) return rc;
+                double cmax = 0;
+                opf_field_t F[1] = {s->C0};
+                opf_range cr = to_c(w);
+                if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &cmax)) return rc;
+                s->affine = cmax != 0.0;
+            }
+        }
         const bool need_diag = s->mg || s->params.precond == OPF_SOLVER_JACOBI || s->params.type == OPF_SOLVER_JACOBI || s->pinned;
         if (need_diag)
             for (int l = 0; l < (int) s->lv.size(); ++l)

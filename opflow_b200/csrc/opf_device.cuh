@@ -1423,22 +1423,25 @@ namespace opf {
         return go(tma_kernel<E, P, A0, CX, BX, BY, STAGES, false, false>);
     }
 
-    template <class E, class P, bool A0>
+    // DIMS: bit (d-1) set <=> fields of dimension d can reach this launcher (the library's builtins serve all three; the
+    // front-end knows its field's dimension at compile time and instantiates only that one)
+    template <class E, class P, bool A0, int DIMS>
     int launch_assign(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
         const LaunchGeom g = assign_geometry(li);
         if (g.grid.x == 0) return 0;
-        if constexpr (E::maxaxis < 1)
+        if constexpr (E::maxaxis < 1 && (DIMS & 1))
             if (li.dim == 1) {
                 assign_kernel<E, P, A0, 1><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
                 return (int) cudaGetLastError();
             }
-        if constexpr (E::maxaxis < 2)
+        if constexpr (E::maxaxis < 2 && (DIMS & 2))
             if (li.dim == 2) {
                 if constexpr (WinInfo<E, A0, 2>::ok && E::nf > 0)
                     if (li.window) return launch_window<E, P, A0, 2>(a, li, st);
                 assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
                 return (int) cudaGetLastError();
             }
+        if constexpr ((DIMS & 4) != 0)
         if (li.dim == 3) {
             if constexpr (WinInfo<E, A0, 3>::ok && E::nf > 0) {
                 // TMA tile skeleton: footprint must fit the ring/box budget (<= 200 KB of shared memory)
@@ -1476,7 +1479,7 @@ namespace opf {
     }
 
     // LaunchInfo.rop < 0 -> assignment; >= 0 -> reduction
-    template <class E>
+    template <class E, int DIMS = 7>
     int launcher(const void* args_blob, const void* launch_blob, void* stream) {
         const ExprArgs& a = *static_cast<const ExprArgs*>(args_blob);
         const LaunchInfo& li = *static_cast<const LaunchInfo*>(launch_blob);
@@ -1488,8 +1491,8 @@ namespace opf {
             return li.mode == 0 ? launch_reduce<E, Exact, false>(a, li, st) : launch_reduce<E, Fast, false>(a, li, st);
         }
         if constexpr (can_alias)
-            if (li.alias0) return li.mode == 0 ? launch_assign<E, Exact, true>(a, li, st) : launch_assign<E, Fast, true>(a, li, st);
-        return li.mode == 0 ? launch_assign<E, Exact, false>(a, li, st) : launch_assign<E, Fast, false>(a, li, st);
+            if (li.alias0) return li.mode == 0 ? launch_assign<E, Exact, true, DIMS>(a, li, st) : launch_assign<E, Fast, true, DIMS>(a, li, st);
+        return li.mode == 0 ? launch_assign<E, Exact, false, DIMS>(a, li, st) : launch_assign<E, Fast, false, DIMS>(a, li, st);
     }
 
 }// namespace opf

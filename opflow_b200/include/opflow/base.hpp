@@ -289,8 +289,4 @@ namespace OpFlow {
     auto rangeReduce(const DS::Range<d>& range, ReOp&& op, F&& func) {
         return rangeReduce_s(range, std::forward<ReOp>(op), std::forward<F>(func));
     }
-    template <std::size_t d, typename ReOp, typename F>
-    auto globalReduce(const DS::Range<d>& range, ReOp&& op, F&& func) {// RangeFor.hpp:125-135: local reduce + allgather; one rank here
-        return rangeReduce_s(range, std::forward<ReOp>(op), std::forward<F>(func));
-    }
 }// namespace OpFlow

@@ -1,0 +1,51 @@
+// opflow/devtypes.hpp -- the device functor node templates the front-end maps expression types onto.
+// Under nvcc the real definitions (functors + kernel skeletons + launcher) come from the engine's opf_device.cuh, and every
+// expression type the program assigns gets its kernels instantiated in the user's translation unit and registered with
+// opf_expr_register.  Under a host-only compiler only the names are declared: the program can then use the expressions
+// libopflow_b200.so carries (opf_expr_builtin_name), anything else fails loudly at run time (OPF_ERR_UNSUPPORTED).
+#pragma once
+#if defined(__CUDACC__) && !defined(OPFLOW_NO_KERNEL_INSTANTIATION)
+#include <opf_device.cuh>
+#define OPFLOW_DEVICE_KERNELS 1
+#else
+namespace opf {
+    template <int K> struct F;
+    template <int K> struct S;
+    template <class L, class R> struct Add;
+    template <class L, class R> struct Sub;
+    template <class L, class R> struct Mul;
+    template <class L, class R> struct Div;
+    template <class L, class R> struct Min;
+    template <class L, class R> struct Max;
+    template <class L, class R> struct Pow;
+    template <class L, class R> struct Lt;
+    template <class L, class R> struct Le;
+    template <class L, class R> struct Gt;
+    template <class L, class R> struct Ge;
+    template <class L, class R> struct Eq;
+    template <class L, class R> struct Ne;
+    template <class L, class R> struct And;
+    template <class L, class R> struct Or;
+    template <class E> struct Neg;
+    template <class E> struct Pos;
+    template <class E> struct Not;
+    template <class E> struct Sqrt;
+    template <class E> struct Abs;
+    template <class E> struct Exp;
+    template <class E> struct Log;
+    template <class E> struct Sin;
+    template <class E> struct Cos;
+    template <class E> struct Tan;
+    template <class E> struct Tanh;
+    template <class E> struct Pow2;
+    template <class C, class A, class B> struct Cond;
+    template <int D, class E> struct D2C;
+    template <int D, class E> struct D1C;
+    template <int D, class E> struct D1Dn;
+    template <int D, class E> struct D1Up;
+    template <int D, class E> struct WenoDn;
+    template <int D, class E> struct WenoUp;
+    template <int D, class E> struct IntpC2N;
+    template <int D, class E> struct IntpN2C;
+}// namespace opf
+#endif

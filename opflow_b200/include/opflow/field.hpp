@@ -1,0 +1,735 @@
+// opflow/field.hpp -- expression templates, operators, CartesianField and ExprBuilder of the B200 front-end.
+//
+// Reference spellings kept:
+//   Expression<Op, Args...>            src/Core/Expr/Expression.hpp:24-111, makeExpression :113-127
+//   scalar wrapping (ScalarExpr)       src/Core/Expr/ScalarExpr.hpp:23-60, BinOpDefMacros.hpp.in:159-191
+//   d1/dx/dy/dz, d2/d2x/d2y/d2z        src/Core/Operator/FDMOperators/DiffsInterface.hpp:21-47
+//   d1IntpCenterToCorner / CornerToCenter   src/Core/Operator/Interpolator/IntpInterface.hpp:26-40
+//   conditional                        src/Core/Operator/Conditional.hpp:72-76
+//   CartesianField / ExprBuilder       src/Core/Field/MeshBased/Structured/CartesianField.hpp:37-1041
+//   FieldAssigner::assign              src/Core/Loops/FieldAssigner.hpp:26-86
+//
+// What differs underneath: an expression is never walked cell by cell on the host.  Its *type* is mapped to a device functor
+// type (opf::Add<opf::F<0>, ...>, opflow_b200/csrc/opf_device.cuh); assignment flattens the leaves (field handles, scalars) in
+// preorder and makes one opf_assign call.  Compiled with nvcc the kernels of every assigned expression type are instantiated in
+// the user's translation unit and registered by signature (opf_expr_register).
+#pragma once
+#include "devtypes.hpp"
+#include "mesh.hpp"
+
+namespace OpFlow {
+    struct ExprTag {};
+    template <typename T>
+    concept ExprType = std::is_base_of_v<ExprTag, std::remove_cvref_t<T>>;
+
+    template <typename D, typename M>
+    struct CartesianField;
+    template <typename F>
+    struct ExprBuilder;
+
+    namespace internal {
+        template <typename T>
+        struct is_cartesian_field : std::false_type {};
+        template <typename D, typename M>
+        struct is_cartesian_field<CartesianField<D, M>> : std::true_type {};
+        template <typename T>
+        concept FieldType = is_cartesian_field<std::remove_cvref_t<T>>::value;
+
+        // leaves of a flattened expression, in preorder (== the numbering of opf::F<k> / opf::S<k> in the device type)
+        struct Flat {
+            std::vector<opf_field_t> fields;
+            std::vector<double> scalars;
+            unsigned mask = 0;// bit k: field leaf k is the equation's unknown
+            std::string sig;
+        };
+    }// namespace internal
+
+    // ScalarExpr<T>::evalAt ignores the index (ScalarExpr.hpp:36)
+    struct ScalarExpr : ExprTag {
+        Real val = 0;
+        static constexpr bool has_unknown = false;
+        static constexpr int dim = 0;
+        template <int NF, int NS>
+        struct Dev {
+            using type = opf::S<NS>;
+            static constexpr int nf = NF, ns = NS + 1;
+        };
+        void flatten(internal::Flat& fl) const {
+            fl.sig += "S<" + std::to_string(fl.scalars.size()) + ">";
+            fl.scalars.push_back(val);
+        }
+    };
+
+    // ExprProxy of an lvalue field (Expr.hpp:322-336): the tree refers to the field, it never copies it
+    template <typename F>
+    struct FieldRef : ExprTag {
+        const F* f = nullptr;
+        static constexpr bool has_unknown = false;
+        static constexpr int dim = F::dim;
+        template <int NF, int NS>
+        struct Dev {
+            using type = opf::F<NF>;
+            static constexpr int nf = NF + 1, ns = NS;
+        };
+        void flatten(internal::Flat& fl) const {
+            f->syncToDevice();
+            fl.sig += "F<" + std::to_string(fl.fields.size()) + ">";
+            fl.fields.push_back(f->h);
+        }
+    };
+
+    // the `e` handed to an equation lambda (reference: StencilField over the target, StencilField.hpp:30-120): here simply a
+    // field leaf flagged as the unknown -- the engine applies the expression to its Krylov vectors instead of assembling rows
+    template <typename F>
+    struct UnknownRef : ExprTag {
+        const F* target = nullptr;
+        static constexpr bool has_unknown = true;
+        static constexpr int dim = F::dim;
+        template <int NF, int NS>
+        struct Dev {
+            using type = opf::F<NF>;
+            static constexpr int nf = NF + 1, ns = NS;
+        };
+        void flatten(internal::Flat& fl) const {
+            fl.mask |= 1u << fl.fields.size();
+            fl.sig += "F<" + std::to_string(fl.fields.size()) + ">";
+            fl.fields.push_back(target->h);
+        }
+    };
+
+    namespace internal {
+        // device types of a pack of children, numbered left to right (preorder)
+        template <int NF, int NS, typename... A>
+        struct DevPack;
+        template <int NF, int NS>
+        struct DevPack<NF, NS> {
+            static constexpr int nf = NF, ns = NS;
+            template <template <class...> class Node>
+            using apply = void;
+        };
+        template <int NF, int NS, typename A0>
+        struct DevPack<NF, NS, A0> {
+            using D0 = typename A0::template Dev<NF, NS>;
+            static constexpr int nf = D0::nf, ns = D0::ns;
+        };
+        template <int NF, int NS, typename A0, typename A1>
+        struct DevPack<NF, NS, A0, A1> {
+            using D0 = typename A0::template Dev<NF, NS>;
+            using D1 = typename A1::template Dev<D0::nf, D0::ns>;
+            static constexpr int nf = D1::nf, ns = D1::ns;
+        };
+        template <int NF, int NS, typename A0, typename A1, typename A2>
+        struct DevPack<NF, NS, A0, A1, A2> {
+            using D0 = typename A0::template Dev<NF, NS>;
+            using D1 = typename A1::template Dev<D0::nf, D0::ns>;
+            using D2 = typename A2::template Dev<D1::nf, D1::ns>;
+            static constexpr int nf = D2::nf, ns = D2::ns;
+        };
+    }// namespace internal
+
+    template <typename Op, typename... Args>
+    struct Expression : ExprTag {
+        std::tuple<Args...> args;
+        static constexpr bool has_unknown = (Args::has_unknown || ...);
+        static constexpr int dim = std::max({Args::dim...});
+        explicit Expression(Args... a) : args(std::move(a)...) {}
+        // Expr::prepare() (Expression.hpp:99-103 + every Op::prepare): ranges and location of the result, computed by the
+        // engine's bit-exact range algebra (opf_expr_prepare) -- host only, no device work
+        mutable DS::Range<(dim > 0 ? dim : 1)> accessibleRange, localRange, logicalRange, assignableRange;
+        mutable std::array<LocOnMesh, (dim > 0 ? dim : 1)> loc {};
+        void prepare() const {
+            if constexpr (dim > 0) {
+                internal::Flat fl;
+                flatten(fl);
+                opf_range r;
+                int l[OPF_MAX_DIM];
+                internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 2, &r, l), "opf_expr_prepare");
+                accessibleRange = internal::from_c<dim>(r);
+                internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 0, &r, nullptr), "opf_expr_prepare");
+                localRange = internal::from_c<dim>(r);
+                internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 3, &r, nullptr), "opf_expr_prepare");
+                logicalRange = internal::from_c<dim>(r);
+                assignableRange.setEmpty();
+                for (int d = 0; d < dim; ++d) loc[d] = static_cast<LocOnMesh>(l[d]);
+            }
+        }
+        template <int NF, int NS>
+        struct Dev {
+            using P = internal::DevPack<NF, NS, Args...>;
+            static constexpr int nf = P::nf, ns = P::ns;
+            static constexpr auto pick() {
+                if constexpr (sizeof...(Args) == 1) return std::type_identity<typename Op::template dev<typename P::D0::type>> {};
+                else if constexpr (sizeof...(Args) == 2)
+                    return std::type_identity<typename Op::template dev<typename P::D0::type, typename P::D1::type>> {};
+                else
+                    return std::type_identity<typename Op::template dev<typename P::D0::type, typename P::D1::type, typename P::D2::type>> {};
+            }
+            using type = typename decltype(pick())::type;
+        };
+        void flatten(internal::Flat& fl) const {
+            fl.sig += Op::name;
+            fl.sig += "<";
+            if constexpr (Op::axis >= 0) fl.sig += std::to_string(Op::axis) + ",";
+            bool first = true;
+            std::apply(
+                    [&](const auto&... a) {
+                        ((fl.sig += (first ? "" : ","), first = false, a.flatten(fl)), ...);
+                    },
+                    args);
+            fl.sig += ">";
+        }
+    };
+
+    namespace internal {
+        template <typename T>
+        auto wrap(T&& t) {
+            using R = std::remove_cvref_t<T>;
+            if constexpr (is_cartesian_field<R>::value) return FieldRef<R> {{}, &t};
+            else if constexpr (std::is_arithmetic_v<R>)
+                return ScalarExpr {{}, static_cast<Real>(t)};
+            else
+                return R(std::forward<T>(t));
+        }
+        template <typename T>
+        using wrapped_t = decltype(wrap(std::declval<T>()));
+
+        template <typename A, typename B>
+        concept ExprOperands = (ExprType<A> || ExprType<B>) && (ExprType<A> || Meta::Numerical<A>) && (ExprType<B> || Meta::Numerical<B>);
+    }// namespace internal
+
+    template <typename Op, typename... T>
+    auto makeExpression(T&&... t) {
+        return Expression<Op, internal::wrapped_t<T>...>(internal::wrap(std::forward<T>(t))...);
+    }
+
+    // ------------------------------------------------------------------------------------------------ point-wise operators
+    // AMDS.hpp / Compare.hpp / Boolean.hpp / MinMax.hpp / Conditional.hpp: `name` is the node name of the signature grammar
+#define OPF_FE_OP2(OpName, Node)                                                                                       \
+    struct OpName {                                                                                                    \
+        static constexpr const char* name = #Node;                                                                     \
+        static constexpr int axis = -1;                                                                                \
+        template <class A, class B>                                                                                    \
+        using dev = opf::Node<A, B>;                                                                                   \
+    };
+#define OPF_FE_OP1(OpName, Node)                                                                                       \
+    struct OpName {                                                                                                    \
+        static constexpr const char* name = #Node;                                                                     \
+        static constexpr int axis = -1;                                                                                \
+        template <class A>                                                                                             \
+        using dev = opf::Node<A>;                                                                                      \
+    };
+    OPF_FE_OP2(AddOp, Add)
+    OPF_FE_OP2(SubOp, Sub)
+    OPF_FE_OP2(MulOp, Mul)
+    OPF_FE_OP2(DivOp, Div)
+    OPF_FE_OP2(MinOp, Min)
+    OPF_FE_OP2(MaxOp, Max)
+    OPF_FE_OP2(PowOp, Pow)
+    OPF_FE_OP2(LessThanOp, Lt)
+    OPF_FE_OP2(LessThanOrEqualOp, Le)
+    OPF_FE_OP2(GreaterThanOp, Gt)
+    OPF_FE_OP2(GreaterThanOrEqualOp, Ge)
+    OPF_FE_OP2(NotEqualToOp, Ne)
+    OPF_FE_OP2(AndOp, And)
+    OPF_FE_OP2(OrOp, Or)
+    OPF_FE_OP1(NegOp, Neg)
+    OPF_FE_OP1(PosOp, Pos)
+    OPF_FE_OP1(NotOp, Not)
+    OPF_FE_OP1(SqrtOp, Sqrt)
+    OPF_FE_OP1(AbsOp, Abs)
+    OPF_FE_OP1(ExpOp, Exp)
+    OPF_FE_OP1(LogOp, Log)
+    OPF_FE_OP1(SinOp, Sin)
+    OPF_FE_OP1(CosOp, Cos)
+    OPF_FE_OP1(TanOp, Tan)
+    OPF_FE_OP1(TanhOp, Tanh)
+    OPF_FE_OP1(Pow2Op, Pow2)
+#undef OPF_FE_OP1
+#undef OPF_FE_OP2
+    struct CondOp {
+        static constexpr const char* name = "Cond";
+        static constexpr int axis = -1;
+        template <class C, class A, class B>
+        using dev = opf::Cond<C, A, B>;
+    };
+
+#define OPF_FE_BINARY(sym, OpName)                                                                                     \
+    template <typename A, typename B>                                                                                  \
+    requires internal::ExprOperands<A, B> auto operator sym(A&& a, B&& b) {                                            \
+        return makeExpression<OpName>(std::forward<A>(a), std::forward<B>(b));                                         \
+    }
+    OPF_FE_BINARY(+, AddOp)
+    OPF_FE_BINARY(-, SubOp)
+    OPF_FE_BINARY(*, MulOp)
+    OPF_FE_BINARY(/, DivOp)
+    OPF_FE_BINARY(<, LessThanOp)
+    OPF_FE_BINARY(<=, LessThanOrEqualOp)
+    OPF_FE_BINARY(>, GreaterThanOp)
+    OPF_FE_BINARY(>=, GreaterThanOrEqualOp)
+    OPF_FE_BINARY(!=, NotEqualToOp)
+    OPF_FE_BINARY(&&, AndOp)
+    OPF_FE_BINARY(||, OrOp)
+#undef OPF_FE_BINARY
+    template <ExprType A>
+    auto operator-(A&& a) {
+        return makeExpression<NegOp>(std::forward<A>(a));
+    }
+    template <ExprType A>
+    auto operator+(A&& a) {
+        return makeExpression<PosOp>(std::forward<A>(a));
+    }
+    template <ExprType A>
+    auto operator!(A&& a) {
+        return makeExpression<NotOp>(std::forward<A>(a));
+    }
+#define OPF_FE_FUNC1(fname, OpName)                                                                                    \
+    template <ExprType A>                                                                                              \
+    auto fname(A&& a) {                                                                                                \
+        return makeExpression<OpName>(std::forward<A>(a));                                                             \
+    }
+    OPF_FE_FUNC1(sqrt, SqrtOp)
+    OPF_FE_FUNC1(abs, AbsOp)
+    OPF_FE_FUNC1(exp, ExpOp)
+    OPF_FE_FUNC1(log, LogOp)
+    OPF_FE_FUNC1(sin, SinOp)
+    OPF_FE_FUNC1(cos, CosOp)
+    OPF_FE_FUNC1(tan, TanOp)
+    OPF_FE_FUNC1(tanh, TanhOp)
+    OPF_FE_FUNC1(pow2, Pow2Op)
+#undef OPF_FE_FUNC1
+    template <typename A, typename B>
+    requires internal::ExprOperands<A, B> auto min(A&& a, B&& b) {
+        return makeExpression<MinOp>(std::forward<A>(a), std::forward<B>(b));
+    }
+    template <typename A, typename B>
+    requires internal::ExprOperands<A, B> auto max(A&& a, B&& b) {
+        return makeExpression<MaxOp>(std::forward<A>(a), std::forward<B>(b));
+    }
+    template <typename A, typename B>
+    requires internal::ExprOperands<A, B> auto pow(A&& a, B&& b) {
+        return makeExpression<PowOp>(std::forward<A>(a), std::forward<B>(b));
+    }
+    template <typename C, typename A, typename B>
+    requires(ExprType<C> || ExprType<A> || ExprType<B>) auto conditional(C&& c, A&& a, B&& b) {
+        return makeExpression<CondOp>(std::forward<C>(c), std::forward<A>(a), std::forward<B>(b));
+    }
+
+    // ------------------------------------------------------------------------------------------------ stencil operators
+#define OPF_FE_STENCIL(KernelName, Node, width)                                                                        \
+    template <std::size_t d>                                                                                           \
+    struct KernelName {                                                                                                \
+        static constexpr const char* name = #Node;                                                                     \
+        static constexpr int axis = static_cast<int>(d);                                                               \
+        static constexpr int bc_width = width;                                                                         \
+        template <class A>                                                                                             \
+        using dev = opf::Node<static_cast<int>(d), A>;                                                                 \
+    };
+    OPF_FE_STENCIL(D2SecondOrderCentered, D2C, 1)        // D2SecondOrderCentered.hpp:22-272
+    OPF_FE_STENCIL(D1FirstOrderCentered, D1C, 1)         // D1FirstOrderCentered.hpp:20-110
+    OPF_FE_STENCIL(D1FirstOrderBiasedDownwind, D1Dn, 1)  // D1FirstOrderBiasedDownwind.hpp:21-170
+    OPF_FE_STENCIL(D1FirstOrderBiasedUpwind, D1Up, 1)    // D1FirstOrderBiasedUpwind.hpp:22-170
+    OPF_FE_STENCIL(D1WENO53Downwind, WenoDn, 3)          // D1WENO53Downwind.hpp:24-200
+    OPF_FE_STENCIL(D1WENO53Upwind, WenoUp, 3)            // D1WENO53Upwind.hpp:24-200
+#undef OPF_FE_STENCIL
+    enum class IntpDirection { Cor2Cen, Cen2Cor };
+    template <std::size_t d, IntpDirection dir>
+    struct D1Linear {// D1Linear.hpp:24-90
+        static constexpr const char* name = dir == IntpDirection::Cen2Cor ? "IntpC2N" : "IntpN2C";
+        static constexpr int axis = static_cast<int>(d);
+        static constexpr int bc_width = 1;
+        template <class A>
+        using dev = std::conditional_t<dir == IntpDirection::Cen2Cor, opf::IntpC2N<static_cast<int>(d), A>, opf::IntpN2C<static_cast<int>(d), A>>;
+    };
+
+    template <typename Kernel, typename E>
+    auto d1(E&& expr) {
+        return makeExpression<Kernel>(std::forward<E>(expr));
+    }
+    template <typename Kernel, typename E>
+    auto d2(E&& expr) {
+        return makeExpression<Kernel>(std::forward<E>(expr));
+    }
+#define OPF_FE_THREED(x_name, y_name, z_name, u_name)                                                                  \
+    template <template <std::size_t> typename Kernel, typename E>                                                      \
+    auto x_name(E&& expr) {                                                                                            \
+        return u_name<Kernel<0>>(std::forward<E>(expr));                                                               \
+    }                                                                                                                  \
+    template <template <std::size_t> typename Kernel, typename E>                                                      \
+    auto y_name(E&& expr) {                                                                                            \
+        return u_name<Kernel<1>>(std::forward<E>(expr));                                                               \
+    }                                                                                                                  \
+    template <template <std::size_t> typename Kernel, typename E>                                                      \
+    auto z_name(E&& expr) {                                                                                            \
+        return u_name<Kernel<2>>(std::forward<E>(expr));                                                               \
+    }
+    OPF_FE_THREED(dx, dy, dz, d1)
+    OPF_FE_THREED(d2x, d2y, d2z, d2)
+#undef OPF_FE_THREED
+    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
+    auto d1IntpCenterToCorner(E&& expr) {
+        return makeExpression<Kernel<dim, IntpDirection::Cen2Cor>>(std::forward<E>(expr));
+    }
+    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
+    auto d1IntpCornerToCenter(E&& expr) {
+        return makeExpression<Kernel<dim, IntpDirection::Cor2Cen>>(std::forward<E>(expr));
+    }
+    template <std::size_t dim, IntpDirection dir, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
+    auto d1Intp(E&& expr) {
+        return makeExpression<Kernel<dim, dir>>(std::forward<E>(expr));
+    }
+
+    // ------------------------------------------------------------------------------------------------ kernel registration
+    namespace internal {
+        template <typename T>
+        struct FieldExprTrait {// FieldExprTrait.hpp: the spellings generic user code reads off a field / expression type
+            static constexpr int dim = std::remove_cvref_t<T>::dim;
+            using elem_type = Real;
+        };
+        // flatten + make sure the expression's kernels are registered with the engine (once per expression type)
+        template <int DIM, typename E>
+        Flat flatten_and_register(const E& e) {
+            Flat fl;
+            e.flatten(fl);
+#ifdef OPFLOW_DEVICE_KERNELS
+            using DevT = typename E::template Dev<0, 0>::type;
+            static const bool once = [&] {// the library's own instantiation (all dimensions) wins if it exists
+                if (!opf_expr_is_registered(fl.sig.c_str()))
+                    check_rc(opf_expr_register(fl.sig.c_str(), &opf::launcher<DevT, 1 << (DIM - 1)>), "opf_expr_register");
+                return true;
+            }();
+            (void) once;
+#endif
+            return fl;
+        }
+    }// namespace internal
+
+    // ------------------------------------------------------------------------------------------------ split strategies
+    struct ParallelPlan;
+    template <typename F>
+    struct AbstractSplitStrategy {// AbstractSplitStrategy.hpp:24-32
+        virtual ~AbstractSplitStrategy() = default;
+        virtual std::string strategyName() const = 0;
+        virtual typename F::RangeType splitRange(const typename F::RangeType& range, const ParallelPlan& plan) = 0;
+        virtual std::vector<typename F::RangeType> getSplitMap(const typename F::RangeType& range, const ParallelPlan& plan) = 0;
+    };
+    inline int getWorkerId();
+    inline int getWorkerCount();
+    inline ParallelPlan& getGlobalParallelPlan();
+
+    // ------------------------------------------------------------------------------------------------ field
+    struct BCInfo {// what ExprBuilder::setBC records per side (BC objects of src/Core/BC/*.hpp reduce to this on the device)
+        BCType type = BCType::Undefined;
+        Real value = 0;
+        BCType getBCType() const { return type; }
+    };
+
+    template <typename D, typename M>
+    struct CartesianField : ExprTag {
+        static_assert(std::is_same_v<D, Real>, "the B200 engine computes in FP64 (Real = double, BasicDataTypes.hpp:30)");
+        static constexpr int dim = M::dim;
+        using RangeType = DS::Range<dim>;
+        using IndexType = DS::MDIndex<dim>;
+        using MeshType = M;
+        using elem_type = D;
+        static constexpr bool has_unknown = false;
+
+        std::string name;
+        M mesh;
+        std::array<LocOnMesh, dim> loc {};
+        std::array<DS::Pair<BCInfo>, dim> bc {};
+        std::array<DS::Pair<int>, dim> ext_width {};
+        int padding = 0;
+        RangeType localRange, assignableRange, accessibleRange, logicalRange, storageRange;
+        std::shared_ptr<AbstractSplitStrategy<CartesianField>> splitStrategy;
+        opf_field_t h = nullptr;
+        bool initialized = false;
+
+        CartesianField() = default;
+        CartesianField(const CartesianField& o) { copyFrom(o); }// deep copy (CartesianField.hpp:57-68)
+        CartesianField(CartesianField&& o) noexcept { moveFrom(std::move(o)); }
+        ~CartesianField() {
+            if (h) opf_field_destroy(h);
+        }
+
+        // ---- assignment (Expr.hpp:53-117 -> assignImpl_final -> FieldAssigner::assign)
+        CartesianField& operator=(const CartesianField& o) {// CartesianField.hpp:180-193
+            if (this == &o) return *this;
+            if (!initialized) {
+                copyFrom(o);
+                return *this;
+            }
+            o.syncToDevice();
+            syncToDevice();
+            internal::check_rc(opf_field_assign_field(h, OPF_OP_EQ, o.h), "opf_field_assign_field");
+            touch();
+            return *this;
+        }
+        CartesianField& operator=(CartesianField&& o) noexcept {
+            if (this != &o) {
+                if (h) opf_field_destroy(h);
+                h = nullptr;
+                moveFrom(std::move(o));
+            }
+            return *this;
+        }
+        template <typename E>
+        requires(ExprType<E> && !internal::FieldType<E>) CartesianField& operator=(const E& e) { return assignExpr(OPF_OP_EQ, e); }
+        template <Meta::Numerical T>
+        CartesianField& operator=(T c) { return assignScalar(OPF_OP_EQ, static_cast<Real>(c)); }
+#define OPF_FE_COMPOUND(sym, OPC)                                                                                      \
+    template <typename E>                                                                                              \
+    requires(ExprType<E> && !internal::FieldType<E>) CartesianField& operator sym(const E& e) { return assignExpr(OPC, e); } \
+    CartesianField& operator sym(const CartesianField& o) {                                                            \
+        o.syncToDevice();                                                                                              \
+        syncToDevice();                                                                                                \
+        internal::check_rc(opf_field_assign_field(h, OPC, o.h), "opf_field_assign_field");                            \
+        touch();                                                                                                       \
+        return *this;                                                                                                  \
+    }                                                                                                                  \
+    template <Meta::Numerical T>                                                                                       \
+    CartesianField& operator sym(T c) { return assignScalar(OPC, static_cast<Real>(c)); }
+        OPF_FE_COMPOUND(+=, OPF_OP_ADD)
+        OPF_FE_COMPOUND(-=, OPF_OP_MINUS)
+        OPF_FE_COMPOUND(*=, OPF_OP_MUL)
+        OPF_FE_COMPOUND(/=, OPF_OP_DIV)
+#undef OPF_FE_COMPOUND
+
+        template <typename E>
+        CartesianField& assignExpr(int op, const E& e) {
+            requireInit("assign an expression to");
+            syncToDevice();
+            auto fl = internal::flatten_and_register<dim>(e);
+            internal::check_rc(opf_assign(h, op, fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), fl.scalars.data(), (int) fl.scalars.size()),
+                               "opf_assign");
+            touch();
+            return *this;
+        }
+        CartesianField& assignScalar(int op, Real c) {// CartesianField.hpp:237-280
+            requireInit("assign a constant to");
+            syncToDevice();
+            internal::check_rc(opf_field_assign_scalar(h, op, c), "opf_field_assign_scalar");
+            touch();
+            return *this;
+        }
+        // CartesianField.hpp:283-294: arbitrary host functor of the physical coordinates (x, or x + dx/2 on Center axes)
+        CartesianField& initBy(const std::function<D(const std::array<Real, dim>&)>& f) {
+            requireInit("initBy");
+            const auto w = DS::commonRange(assignableRange, localRange);
+            if (w.count() > 0) {
+                std::vector<Real> vals((std::size_t) w.count());
+                std::size_t n = 0;
+                rangeFor_s(w, [&](auto&& i) {
+                    std::array<Real, dim> c;
+                    for (int k = 0; k < dim; ++k) c[k] = loc[k] == LocOnMesh::Corner ? mesh.x(k, i[k]) : mesh.x(k, i[k]) + .5 * mesh.dx(k, i[k]);
+                    vals[n++] = f(c);
+                });
+                const opf_range r = internal::to_c(w);
+                internal::check_rc(opf_field_upload(h, &r, vals.data()), "opf_field_upload");
+            }
+            touch();
+            return updatePadding();
+        }
+        CartesianField& updatePadding() {
+            requireInit("updatePadding");
+            syncToDevice();
+            internal::check_rc(opf_field_update_padding(h), "opf_field_update_padding");
+            touch();
+            return *this;
+        }
+        void prepare() const {}
+        const M& getMesh() const { return mesh; }
+        auto getLocalWritableRange() const { return DS::commonRange(assignableRange, localRange); }
+        auto getLocalReadableRange() const {
+            opf_range r;
+            internal::check_rc(opf_field_get_range(h, 5, &r), "opf_field_get_range");
+            return internal::from_c<dim>(r);
+        }
+        const auto& getName() const { return name; }
+
+        // ---- host access: a lazily synchronised mirror of the device storage (user lambdas in rangeFor / rangeReduce, writers)
+        Real evalAt(const IndexType& i) const { return hostRef(i); }
+        Real operator[](const IndexType& i) const { return hostRef(i); }
+        Real& operator[](const IndexType& i) {
+            Real& r = hostRef(i);
+            host_dirty = true;
+            return r;
+        }
+        Real operator()(const IndexType& i) const { return hostRef(i); }
+        bool contains(const CartesianField& o) const { return this == &o; }
+        // mirror -> device if host code wrote through operator[] (whole storage, no updatePadding: PlainTensor semantics)
+        void syncToDevice() const {
+            if (!host_dirty) return;
+            const opf_range r = internal::to_c(storageRange);
+            internal::check_rc(opf_field_upload(h, &r, mirror.data()), "opf_field_upload");
+            host_dirty = false;
+        }
+        void touch() const { mirror_valid = false; }// device data changed
+
+    private:
+        template <typename>
+        friend struct ExprBuilder;
+        mutable std::vector<Real> mirror;
+        mutable bool mirror_valid = false, host_dirty = false;
+
+        void requireInit(const char* what) const {
+            if (!initialized || !h) {
+                OP_CRITICAL("CartesianField not initialized. Cannot {} it.", what);
+                OP_ABORT;
+            }
+        }
+        Real& hostRef(const IndexType& i) const {
+            requireInit("read");
+            if (!mirror_valid) {
+                mirror.resize((std::size_t) storageRange.count());
+                const opf_range r = internal::to_c(storageRange);
+                internal::check_rc(opf_field_download(h, &r, mirror.data()), "opf_field_download");
+                mirror_valid = true;
+            }
+            std::size_t off = 0, stride = 1;
+            for (int d = 0; d < dim; ++d) {
+                off += (std::size_t)(i[d] - storageRange.start[d]) * stride;
+                stride *= (std::size_t)(storageRange.end[d] - storageRange.start[d]);
+            }
+            return mirror[off];
+        }
+        void copyMeta(const CartesianField& o) {
+            name = o.name;
+            mesh = o.mesh;
+            loc = o.loc;
+            bc = o.bc;
+            ext_width = o.ext_width;
+            padding = o.padding;
+            localRange = o.localRange;
+            assignableRange = o.assignableRange;
+            accessibleRange = o.accessibleRange;
+            logicalRange = o.logicalRange;
+            storageRange = o.storageRange;
+            splitStrategy = o.splitStrategy;
+            initialized = o.initialized;
+        }
+        void copyFrom(const CartesianField& o) {
+            if (h) opf_field_destroy(h);
+            h = nullptr;
+            copyMeta(o);
+            mirror_valid = host_dirty = false;
+            if (o.h) {
+                o.syncToDevice();
+                h = internal::check_ptr(opf_field_clone(o.h, name.c_str()), "opf_field_clone");
+            }
+        }
+        void moveFrom(CartesianField&& o) {
+            copyMeta(o);
+            h = o.h;
+            o.h = nullptr;
+            o.initialized = false;
+            mirror = std::move(o.mirror);
+            mirror_valid = o.mirror_valid;
+            host_dirty = o.host_dirty;
+        }
+    };
+
+    // ExprBuilder<CartesianField> (CartesianField.hpp:796-1033).  Like the reference, a builder keeps its settings between
+    // build() calls and build() hands out a reference to its internal field (callers copy-construct from it).
+    template <typename D, typename M>
+    struct ExprBuilder<CartesianField<D, M>> {
+        using Field = CartesianField<D, M>;
+        static constexpr int dim = Field::dim;
+        Field f;
+
+        ExprBuilder() = default;
+        auto& setName(const std::string& n) {
+            f.name = n;
+            return *this;
+        }
+        auto& setMesh(const M& m) {
+            f.mesh = m;
+            return *this;
+        }
+        auto& setLoc(const std::array<LocOnMesh, dim>& l) {
+            f.loc = l;
+            return *this;
+        }
+        auto& setLoc(LocOnMesh l) {
+            f.loc.fill(l);
+            return *this;
+        }
+        auto& setLocOfDim(int i, LocOnMesh l) {
+            f.loc[i] = l;
+            return *this;
+        }
+        // setBC(d, pos, type) for logical BCs, setBC(d, pos, type, value) for Dirc / Neum (CartesianField.hpp:827-895)
+        auto& setBC(int d, DimPos pos, BCType type) {
+            (pos == DimPos::start ? f.bc[d].start : f.bc[d].end) = BCInfo {type, 0.};
+            if (type == BCType::Periodic) f.bc[d].start = f.bc[d].end = BCInfo {type, 0.};
+            return *this;
+        }
+        template <Meta::Numerical T>
+        auto& setBC(int d, DimPos pos, BCType type, T val) {
+            if (type != BCType::Dirc && type != BCType::Neum) {
+                OP_ERROR("BC type not supported.");
+                OP_ABORT;
+            }
+            (pos == DimPos::start ? f.bc[d].start : f.bc[d].end) = BCInfo {type, static_cast<Real>(val)};
+            return *this;
+        }
+        auto& setExt(int d, DimPos pos, int width) {
+            (pos == DimPos::start ? f.ext_width[d].start : f.ext_width[d].end) = width;
+            return *this;
+        }
+        auto& setExt(int width) {
+            for (auto& e : f.ext_width) e.start = e.end = width;
+            return *this;
+        }
+        auto& setPadding(int p) {
+            f.padding = p;
+            return *this;
+        }
+        auto& setSplitStrategy(std::shared_ptr<AbstractSplitStrategy<Field>> s) {
+            f.splitStrategy = std::move(s);
+            return *this;
+        }
+
+        auto& build() {// calculateRanges + validateRanges + storage + updatePadding happen in opf_field_create
+            if (!f.mesh.h()) {
+                OP_CRITICAL("ExprBuilder: setMesh() missing for field '{}'", f.name);
+                OP_ABORT;
+            }
+            opf_field_desc d {};
+            d.mesh = f.mesh.h();
+            for (int k = 0; k < dim; ++k) {
+                d.loc[k] = static_cast<int>(f.loc[k]);
+                d.bc[k][0].type = static_cast<int>(f.bc[k].start.type);
+                d.bc[k][0].value = f.bc[k].start.value;
+                d.bc[k][1].type = static_cast<int>(f.bc[k].end.type);
+                d.bc[k][1].value = f.bc[k].end.value;
+                d.ext[k][0] = f.ext_width[k].start;
+                d.ext[k][1] = f.ext_width[k].end;
+            }
+            d.padding = f.padding;
+            std::vector<opf_range> split;
+            if (f.splitStrategy && getWorkerCount() > 1) {
+                auto map = f.splitStrategy->getSplitMap(f.mesh.getRange(), getGlobalParallelPlan());
+                for (auto& r : map) split.push_back(internal::to_c(r));
+                d.n_ranks = (int) split.size();
+                d.rank = getWorkerId();
+                d.split_map = split.data();
+            }
+            if (f.h) opf_field_destroy(f.h);
+            f.h = internal::check_ptr(opf_field_create(&d, f.name.c_str()), "opf_field_create");
+            auto get = [&](int which) {
+                opf_range r;
+                internal::check_rc(opf_field_get_range(f.h, which, &r), "opf_field_get_range");
+                return internal::from_c<dim>(r);
+            };
+            f.localRange = get(0);
+            f.assignableRange = get(1);
+            f.accessibleRange = get(2);
+            f.logicalRange = get(3);
+            f.storageRange = get(4);
+            f.padding = opf_field_padding(f.h);
+            f.initialized = true;
+            f.mirror_valid = f.host_dirty = false;
+            return f;
+        }
+    };
+}// namespace OpFlow

