@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define OPF_MAX_DIM 3
-#define OPF_MAX_FIELDS 16  /* field leaves per expression  */
+#define OPF_MAX_FIELDS 32  /* field leaves per expression  */
 #define OPF_MAX_SCALARS 16 /* scalar leaves per expression */
 #define OPF_MAX_NODES 96   /* tree nodes per expression    */
 

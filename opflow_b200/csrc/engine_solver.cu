@@ -267,14 +267,15 @@ namespace {
         return opf_assign_ex(dst, OPF_OP_EQ, sig, F, nf, S, ns, OPF_ASSIGN_NO_PADDING);
     }
     // q = lhs(in): ghost fill of `in` with its (homogeneous) BCs, then the expression functor
-    int apply_lhs(Solver* s, opf_field_s* in, opf_field_s* out, int level, bool pin = true) {
+    // raw: the expression itself, constant part included (used once per solve to build b)
+    int apply_lhs(Solver* s, opf_field_s* in, opf_field_s* out, int level, bool pin = true, bool raw = false) {
         if (int rc = field_update_padding(in)) return rc;
         opf_field_t F[OPF_MAX_FIELDS];
         const int nf = (int) s->lhs_fields.size();
         for (int k = 0; k < nf; ++k) F[k] = ((s->mask >> k) & 1u) ? in : s->lhs_fields[k];
         if (int rc = opf_assign_ex(out, OPF_OP_EQ, s->lhs_sig.c_str(), F, nf, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING))
             return rc;
-        if (s->affine && level == 0)
+        if (s->affine && level == 0 && !raw)
             if (int rc = assign(out, "Sub<F<0>,F<1>>", {out, s->C0}, {})) return rc;
         if (s->pin_active && pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
             copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(out->biased(out->cur), in->biased(in->cur), s->lv[level].pin_off);
@@ -517,8 +518,12 @@ extern "C" {
 
 opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, const opf_field_t* lhs_fields, int n_lhs_fields,
                                const double* lhs_scalars, int n_lhs_scalars, unsigned unknown_mask, const opf_solver_params* params) {
-    if (!target || !lhs_signature || !params || n_lhs_fields > OPF_MAX_FIELDS - 1) {
-        fail(OPF_ERR_INVALID, "opf_solver_create: bad arguments");
+    if (!target || !lhs_signature || !params) {
+        fail(OPF_ERR_INVALID, "opf_solver_create: null argument");
+        return nullptr;
+    }
+    if (n_lhs_fields > OPF_MAX_FIELDS - 1) {
+        fail(OPF_ERR_UNSUPPORTED, "opf_solver_create: the equation has %d field leaves (max %d)", n_lhs_fields, OPF_MAX_FIELDS - 1);
         return nullptr;
     }
     if (require_device()) return nullptr;
@@ -739,7 +744,11 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
                 s->affine = cmax != 0.0;
             }
         }
-        const bool need_diag = s->mg || s->params.precond == OPF_SOLVER_JACOBI || s->params.type == OPF_SOLVER_JACOBI || s->pinned;
+        // a multigrid request on an operator that cannot be coarsened (coefficient fields, decomposed target) degrades to its
+        // level-0 smoother, i.e. Jacobi: the diagonal is needed then as well
+        const bool wants_mg = s->params.precond == OPF_SOLVER_PFMG || s->params.precond == OPF_SOLVER_SMG || s->params.type == OPF_SOLVER_PFMG
+                              || s->params.type == OPF_SOLVER_SMG;
+        const bool need_diag = s->mg || wants_mg || s->params.precond == OPF_SOLVER_JACOBI || s->params.type == OPF_SOLVER_JACOBI || s->pinned;
         if (need_diag)
             for (int l = 0; l < (int) s->lv.size(); ++l)
                 if (l == 0 || s->mg)
@@ -764,7 +773,7 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     s->pin_active = false;
     if (int rc = opf_assign_ex(s->B, OPF_OP_EQ, rhs_signature, rhs_fields, n_rhs_fields, rhs_scalars, n_rhs_scalars, OPF_ASSIGN_NO_PADDING)) return rc;
     if (int rc = assign(s->E0, "S<0>", {}, {0.0})) return rc;
-    if (int rc = apply_lhs(s, s->E0, s->Q, 0, false)) return rc;// E0 keeps the target's real BCs: its ghosts carry the boundary data
+    if (int rc = apply_lhs(s, s->E0, s->Q, 0, false, true)) return rc;// E0 keeps the target's real BCs: its ghosts carry the boundary data
     if (int rc = assign(s->B, "Sub<F<0>,F<1>>", {s->B, s->Q}, {})) return rc;
     // ---- x0 = current target values (initx :119-123)
     if (int rc = assign(s->X, "F<0>", {t}, {})) return rc;
@@ -775,6 +784,8 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     double rel = 0;
     auto finish = [&](int rc_in) {
         if (rc_in) return rc_in;
+        static const bool dbg = getenv("OPF_SOLVER_DEBUG") != nullptr;
+        if (dbg) fprintf(stderr, "[opf_solver] target=%s lhs=%s type=%d precond=%d mg=%d affine=%d pinned=%d singular=%d |b|=%.6e iters=%d rel=%.3e\n", t->name.c_str(), s->lhs_sig.substr(0, 40).c_str(), s->params.type, s->params.precond, (int) s->mg, (int) s->affine, (int) s->pinned, (int) s->singular, bnorm, iters, rel);
         if (state) {
             state->niter = iters;
             state->relerr = rel;

@@ -19,7 +19,7 @@
 
 namespace opf {
 
-    constexpr int MAX_FIELDS = 16;
+    constexpr int MAX_FIELDS = 32;
     constexpr int MAX_SCALARS = 16;
     constexpr int MAX_NODES = 96;
 

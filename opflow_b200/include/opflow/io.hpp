@@ -4,6 +4,7 @@
 // link against in this build, so it writes the same records as raw little-endian blocks (<name>.h5.raw + a text index).
 #pragma once
 #include "field.hpp"
+#include <iomanip>
 
 namespace OpFlow::Utils {
     struct TimeStamp {
@@ -20,45 +21,68 @@ namespace OpFlow::Utils {
         }
     }// namespace detail
 
+    // TecplotASCIIStream (TecplotASCIIStream.hpp:36-215): same on-disk layout -- one ORDERED / BLOCK zone per `<<`, coordinates of
+    // the first zone only when the mesh is fixed (default), values with 10 digits
     struct TecplotASCIIStream {
         std::string path;
         std::ofstream of;
         TimeStamp time;
-        bool alwaysWriteMesh = true, writeMesh = true, separate = false;
+        bool writeMesh = true, fixed_mesh = true, separate_file = false;
         TecplotASCIIStream() = default;
         explicit TecplotASCIIStream(const std::string& p) : path(p), of(p) {}
         auto& operator<<(const TimeStamp& t) {
             time = t;
             return *this;
         }
-        auto& alwaysWriteMeshes(bool o) {
-            alwaysWriteMesh = o;
-            return *this;
-        }
+        // the reference's flag reads inverted (`fixed_mesh` true == write the coordinates in every zone, its default;
+        // fixedMesh() clears it: TecplotASCIIStream.hpp:51,119) -- kept, so files have the same zones
         auto& fixedMesh() {
-            alwaysWriteMesh = false;
+            fixed_mesh = false;
             return *this;
         }
         auto& dumpToSeparateFile() {
-            separate = true;
+            separate_file = true;
+            if (!fixed_mesh) fixed_mesh = true;
             return *this;
         }
         void close() { of.close(); }
         template <internal::FieldType F>
         auto& operator<<(const F& f) {
             constexpr int dim = F::dim;
-            static const char* xn[3] = {"X", "Y", "Z"};
-            of << "TITLE = \"Solution of " << f.name << "\"\nVARIABLES = ";
-            for (int d = 0; d < dim; ++d) of << "\"" << xn[d] << "\", ";
-            of << "\"" << f.name << "\"\nZONE T=\"t=" << time.time << "\" ";
+            if (separate_file) {
+                std::string filename = path, ext;
+                if (auto dot = filename.rfind('.'); dot != std::string::npos) {
+                    ext = filename.substr(dot);
+                    filename.erase(dot);
+                }
+                of.close();
+                of.open(filename + std::format("_{:.6f}", time.time) + ext, std::ofstream::out | std::ofstream::ate);
+            }
+            if (of.tellp() == 0) {
+                of << std::format("TITLE = \"Solution of {} \"\n", f.name);
+                static const char* vars[3] = {R"("X")", R"("X", "Y")", R"("X", "Y", "Z")"};
+                of << std::format("VARIABLES = {}, \"{}\"\n", vars[dim - 1], f.name);
+            }
+            of << "ZONE\nZONETYPE = ORDERED DATAPACKING = BLOCK\n";
             static const char* in[3] = {"I", "J", "K"};
-            for (int d = 0; d < dim; ++d) of << in[d] << "=" << (f.localRange.end[d] - f.localRange.start[d]) << " ";
-            of << "SOLUTIONTIME=" << time.time << " DATAPACKING=POINT\n";
-            of << std::scientific;
-            rangeFor_s(f.localRange, [&](auto&& i) {
-                for (int d = 0; d < dim; ++d) of << (f.loc[d] == LocOnMesh::Corner ? f.mesh.x(d, i[d]) : f.mesh.x(d, i[d]) + .5 * f.mesh.dx(d, i[d])) << " ";
-                of << f.evalAt(i) << "\n";
-            });
+            for (int d = 0; d < dim; ++d) of << (d ? " " : "") << in[d] << " = " << (f.localRange.end[d] - f.localRange.start[d]);
+            of << "\n" << std::scientific << std::setprecision(10);
+            of << std::format("SOLUTIONTIME = {}\n", time.time);
+            if (!writeMesh) {
+                if constexpr (dim == 1) of << "VARSHARELIST=([1]=1)\n";
+                else
+                    of << std::format("VARSHARELIST=([1-{}]=1)\n", dim);
+            } else {
+                for (int k = 0; k < dim; ++k) {
+                    if (f.loc[k] == LocOnMesh::Corner) rangeFor_s(f.localRange, [&](auto&& i) { of << f.mesh.x(k, i[k]) << "\n"; });
+                    else
+                        rangeFor_s(f.localRange, [&](auto&& i) { of << Math::mid(f.mesh.x(k, i[k]), f.mesh.x(k, i[k] + 1)) << "\n"; });
+                }
+            }
+            rangeFor_s(f.localRange, [&](auto&& i) { of << f.evalAt(i) << "\n"; });
+            of.flush();
+            if (!separate_file) writeMesh = fixed_mesh;
+            if (separate_file) close();
             return *this;
         }
     };
