@@ -65,10 +65,11 @@ namespace {
     // coarse = R fine with R = (1/2) P^T per axis: node-centred (1/4, 1/2, 1/4) full weighting; cell-centred
     // (1/8, 3/8, 3/8, 1/8) over fine cells 2I-1 .. 2I+2 (wall-adjusted like the prolongation).
     __global__ void __launch_bounds__(256) restrict_kernel(const XferParams p) {
-        const long long n0 = p.chi[0] - p.clo[0], n1 = p.chi[1] - p.clo[1], n2 = p.chi[2] - p.clo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            int I[3] = {p.clo[0] + (int) (t % n0), p.clo[1] + (int) ((t / n0) % n1), p.clo[2] + (int) (t / (n0 * n1))};
+        // one thread per coarse cell; rows / planes come from the grid (no 64-bit divisions), axis 0 is coalesced
+        {
+            const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+            if (x0 >= p.chi[0] - p.clo[0]) return;
+            int I[3] = {p.clo[0] + x0, p.clo[1] + (int) blockIdx.y, p.clo[2] + (int) blockIdx.z};
             int idx[3][4], cnt[3];
             double wgt[3][4];
             for (int d = 0; d < 3; ++d) {
@@ -117,10 +118,10 @@ namespace {
     // weights (3/4 parent, 1/4 neighbouring coarse cell).  A neighbour beyond a wall is the homogeneous ghost value of the
     // coarse correction: +parent for Neumann/Symm, -parent for Dirichlet/ASymm.
     __global__ void __launch_bounds__(256) prolong_kernel(const XferParams p) {
-        const long long n0 = p.fhi[0] - p.flo[0], n1 = p.fhi[1] - p.flo[1], n2 = p.fhi[2] - p.flo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            int g[3] = {p.flo[0] + (int) (t % n0), p.flo[1] + (int) ((t / n0) % n1), p.flo[2] + (int) (t / (n0 * n1))};
+        {
+            const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+            if (x0 >= p.fhi[0] - p.flo[0]) return;
+            int g[3] = {p.flo[0] + x0, p.flo[1] + (int) blockIdx.y, p.flo[2] + (int) blockIdx.z};
             int idx[3][2], cnt[3];
             double wgt[3][2];
             for (int d = 0; d < 3; ++d) {
@@ -164,10 +165,10 @@ namespace {
     };
     __global__ void __launch_bounds__(256) color_fill_kernel(double* u, long long s1, long long s2, opf::LaunchRange r, int dim, Mod3 mm, int c0, int c1,
                                                              int c2) {
-        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            const int i = r.lo[0] + (int) (t % n0), j = r.lo[1] + (int) ((t / n0) % n1), k = r.lo[2] + (int) (t / (n0 * n1));
+        {
+            const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+            if (x0 >= r.hi[0] - r.lo[0]) return;
+            const int i = r.lo[0] + x0, j = r.lo[1] + (int) blockIdx.y, k = r.lo[2] + (int) blockIdx.z;
             const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
                             && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
             u[(long long) i + (long long) j * s1 + (long long) k * s2] = on ? 1.0 : 0.0;
@@ -175,10 +176,10 @@ namespace {
     }
     __global__ void __launch_bounds__(256) color_recip_kernel(const double* q, double* dinv, long long s1, long long s2, opf::LaunchRange r, int dim,
                                                               Mod3 mm, int c0, int c1, int c2) {
-        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            const int i = r.lo[0] + (int) (t % n0), j = r.lo[1] + (int) ((t / n0) % n1), k = r.lo[2] + (int) (t / (n0 * n1));
+        {
+            const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+            if (x0 >= r.hi[0] - r.lo[0]) return;
+            const int i = r.lo[0] + x0, j = r.lo[1] + (int) blockIdx.y, k = r.lo[2] + (int) blockIdx.z;
             const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
                             && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
             if (on) {
@@ -191,18 +192,25 @@ namespace {
     // u -= sum[0] / n over a box: projects a coarse right-hand side onto the range of a singular (all-Neumann / periodic)
     // operator without a host round trip (sum[0] was produced by the reduction kernels on the same stream)
     __global__ void __launch_bounds__(256) sub_mean_kernel(double* u, long long s1, long long s2, opf::LaunchRange r, const double* sum, double inv_n) {
-        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
-        const long long total = n0 * n1 * n2;
         const double m = sum[0] * inv_n;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            const long long o = (r.lo[0] + t % n0) + (r.lo[1] + (t / n0) % n1) * s1 + (r.lo[2] + t / (n0 * n1)) * s2;
-            u[o] -= m;
-        }
+        const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x0 >= r.hi[0] - r.lo[0]) return;
+        const long long o = (long long) (r.lo[0] + x0) + (long long) (r.lo[1] + (int) blockIdx.y) * s1 + (long long) (r.lo[2] + (int) blockIdx.z) * s2;
+        u[o] -= m;
     }
     __global__ void set_cell_kernel(double* u, long long off, double v) { u[off] = v; }
     __global__ void copy_cell_kernel(double* dst, const double* src, long long off) { dst[off] = src[off]; }
 
-    int blocks_for(long long total) { return (int) std::max<long long>(1, std::min<long long>((total + 255) / 256, 8LL * ctx().sm_count)); }
+    // box launch: threads along axis 0, rows and planes from blockIdx.y / .z
+    struct BoxGrid {
+        dim3 grid, block;
+    };
+    BoxGrid box_grid(const Range& w) {
+        const int n0 = std::max(1, w.end[0] - w.start[0]), n1 = std::max(1, w.end[1] - w.start[1]), n2 = std::max(1, w.end[2] - w.start[2]);
+        int bs = 256;
+        while (bs > 32 && bs / 2 >= n0) bs >>= 1;
+        return BoxGrid{dim3((n0 + bs - 1) / bs, n1, n2), dim3(bs, 1, 1)};
+    }
     opf::LaunchRange lr_of(const Range& r) {
         opf::LaunchRange o;
         for (int d = 0; d < 3; ++d) o.lo[d] = r.start[d], o.hi[d] = r.end[d];
@@ -230,6 +238,15 @@ struct opf_solver_s {
     // contain e) is affine: lhs(p) = A.p + c.  C0 = lhs(0 with homogeneous BCs) = c is removed from every operator application.
     opf_field_s* C0 = nullptr;
     bool affine = false;
+    // the multigrid preconditioner M^-1 r -> z is a fixed sequence of ~250 small launches (12 levels at 4097^2) with no host
+    // decision inside: after a warm-up call it is captured once per (r, z) pair into a CUDA graph and replayed
+    struct VGraph {
+        opf_field_s *r, *z;
+        cudaGraphExec_t exec;
+        long long launches;
+        int calls;
+    };
+    std::vector<VGraph> vgraphs;
     bool pinned = false;
     long long pin_off = 0;
     bool setup_done = false, mg = false, has_res_sig = false;
@@ -322,14 +339,14 @@ namespace {
             }
         }
         const opf::LaunchRange r = lr_of(L.w);
-        const int nb = blocks_for(L.w.count());
+        const BoxGrid bg = box_grid(L.w);
         for (int c2 = 0; c2 < mm.m[2]; ++c2)
             for (int c1 = 0; c1 < mm.m[1]; ++c1)
                 for (int c0 = 0; c0 < mm.m[0]; ++c0) {
-                    color_fill_kernel<<<nb, 256, 0, ctx().stream>>>(L.x->biased(L.x->cur), L.x->pitch1, L.x->pitch2, r, dim, mm, c0, c1, c2);
+                    color_fill_kernel<<<bg.grid, bg.block, 0, ctx().stream>>>(L.x->biased(L.x->cur), L.x->pitch1, L.x->pitch2, r, dim, mm, c0, c1, c2);
                     ctx().launches++;
                     if (int rc = apply_lhs(s, L.x, L.q, level, false)) return rc;
-                    color_recip_kernel<<<nb, 256, 0, ctx().stream>>>(L.q->biased(L.q->cur), L.dinv->biased(L.dinv->cur), L.dinv->pitch1, L.dinv->pitch2, r,
+                    color_recip_kernel<<<bg.grid, bg.block, 0, ctx().stream>>>(L.q->biased(L.q->cur), L.dinv->biased(L.dinv->cur), L.dinv->pitch1, L.dinv->pitch2, r,
                                                                      dim, mm, c0, c1, c2);
                     ctx().launches++;
                 }
@@ -376,7 +393,7 @@ namespace {
     int project_mean(Solver* s, opf_field_s* f, const Range& w) {
         double* dev = nullptr;
         if (int rc = reduce_sum_device(f, w, &dev)) return rc;
-        sub_mean_kernel<<<blocks_for(w.count()), 256, 0, ctx().stream>>>(f->biased(f->cur), f->pitch1, f->pitch2, lr_of(w), dev, 1.0 / (double) w.count());
+        sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(f->biased(f->cur), f->pitch1, f->pitch2, lr_of(w), dev, 1.0 / (double) w.count());
         ctx().launches++;
         return OPF_OK;
     }
@@ -386,7 +403,8 @@ namespace {
         const int last = (int) s->lv.size() - 1;
         if (s->singular)
             if (int rc = project_mean(s, L.b, L.w)) return rc;
-        if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : 24, zero_guess);
+        static const int coarse_sweeps = getenv("OPF_MG_COARSE_SWEEPS") ? atoi(getenv("OPF_MG_COARSE_SWEEPS")) : 8;
+        if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : coarse_sweeps, zero_guess);
         const int pre = std::max(1, s->params.num_pre_relax), post = std::max(1, s->params.num_post_relax);
         if (int rc = smooth(s, level, pre, zero_guess)) return rc;
         if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
@@ -394,12 +412,12 @@ namespace {
         XferParams p = xfer(s, level);
         p.fine = L.r->biased(L.r->cur), p.fs1 = L.r->pitch1, p.fs2 = L.r->pitch2;
         p.coarse = C.b->biased(C.b->cur), p.cs1 = C.b->pitch1, p.cs2 = C.b->pitch2;
-        restrict_kernel<<<blocks_for(C.w.count()), 256, 0, ctx().stream>>>(p);
+        restrict_kernel<<<box_grid(C.w).grid, box_grid(C.w).block, 0, ctx().stream>>>(p);
         ctx().launches++;
         if (int rc = vcycle(s, level + 1, true)) return rc;
         p.fine = L.x->biased(L.x->cur), p.fs1 = L.x->pitch1, p.fs2 = L.x->pitch2;
         p.coarse = C.x->biased(C.x->cur), p.cs1 = C.x->pitch1, p.cs2 = C.x->pitch2;
-        prolong_kernel<<<blocks_for(L.w.count()), 256, 0, ctx().stream>>>(p);
+        prolong_kernel<<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
         return smooth(s, level, post, false);
@@ -412,11 +430,50 @@ namespace {
         switch (s->params.precond) {
             case OPF_SOLVER_PFMG:
             case OPF_SOLVER_SMG: {
-                if (int rc = assign(L0.b, "F<0>", {r}, {})) return rc;
-                const int cycles = std::max(1, s->params.precond_max_iter);
-                for (int c = 0; c < cycles; ++c)
-                    if (int rc = vcycle(s, 0, c == 0)) return rc;
-                return assign(z, "F<0>", {L0.x}, {});
+                auto body = [&]() -> int {
+                    if (int rc = assign(L0.b, "F<0>", {r}, {})) return rc;
+                    const int cycles = std::max(1, s->params.precond_max_iter);
+                    for (int c = 0; c < cycles; ++c)
+                        if (int rc = vcycle(s, 0, c == 0)) return rc;
+                    return assign(z, "F<0>", {L0.x}, {});
+                };
+                static const int graphs_on = getenv("OPF_GRAPHS") ? atoi(getenv("OPF_GRAPHS")) : 1;
+                if (!graphs_on) return body();
+                Solver::VGraph* g = nullptr;
+                for (auto& e : s->vgraphs)
+                    if (e.r == r && e.z == z) g = &e;
+                if (!g) {
+                    s->vgraphs.push_back(Solver::VGraph{r, z, nullptr, 0, 0});
+                    g = &s->vgraphs.back();
+                }
+                Context& c = ctx();
+                if (g->exec) {
+                    OPF_CUDA(cudaGraphLaunch(g->exec, c.stream));
+                    c.launches += g->launches;
+                    return OPF_OK;
+                }
+                if (++g->calls < 2) return body();// first call: allocations, kernel attribute set-up, BC-clean flags settle
+                const long long l0 = c.launches;
+                OPF_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = body();
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
+                if (rc) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc;
+                }
+                if (ce != cudaSuccess || !graph) return fail(OPF_ERR_CUDA, "V-cycle graph capture failed: %s", cudaGetErrorString(ce));
+                g->launches = c.launches - l0;
+                c.launches = l0;
+                const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) {
+                    g->exec = nullptr;
+                    return fail(OPF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+                }
+                OPF_CUDA(cudaGraphLaunch(g->exec, c.stream));
+                c.launches += g->launches;
+                return OPF_OK;
             }
             case OPF_SOLVER_JACOBI: return assign(z, "Mul<F<0>,F<1>>", {L0.dinv, r}, {});
             default: return assign(z, "F<0>", {r}, {});
@@ -595,6 +652,7 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
     return s;
 }
 
+static void drop_graphs(opf_solver_s* s);
 int opf_solver_levels(opf_solver_t s) { return s ? (int) s->lv.size() : -1; }
 
 int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_fields, const double* lhs_scalars, int n_lhs_scalars) {
@@ -612,12 +670,23 @@ int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_f
         if (lhs_scalars[k] != s->lhs_scalars[k]) changed = true;
         s->lhs_scalars[k] = lhs_scalars[k];
     }
-    if (changed) s->setup_done = false;// a static operator with new coefficients is set up again
+    if (changed) {
+        s->setup_done = false;// a static operator with new coefficients is set up again
+        drop_graphs(s);       // scalars and field pointers are baked into the captured launches
+    }
     return OPF_OK;
+}
+
+static void drop_graphs(opf_solver_s* s) {
+    if (opfe::ctx().inited) cudaStreamSynchronize(opfe::ctx().stream);
+    for (auto& g : s->vgraphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->vgraphs.clear();
 }
 
 int opf_solver_destroy(opf_solver_t s) {
     if (!s) return OPF_OK;
+    drop_graphs(s);
     for (auto& L : s->lv) free_level_fields(L);
     for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0, s->C0})
         if (f) opf_field_destroy(f);
@@ -807,7 +876,7 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
         if (int rc = project_mean(s, s->B, w)) return rc;
         if (int rc = run_iteration(s, type, w, bnorm, tol, maxit, &iters, &rel)) return rc;
         copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(s->Q->biased(s->Q->cur), s->X->biased(s->X->cur), s->pin_off);
-        sub_mean_kernel<<<blocks_for(w.count()), 256, 0, ctx().stream>>>(s->X->biased(s->X->cur), s->X->pitch1, s->X->pitch2, lr_of(w),
+        sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(s->X->biased(s->X->cur), s->X->pitch1, s->X->pitch2, lr_of(w),
                                                                          s->Q->biased(s->Q->cur) + s->pin_off, 1.0);
         ctx().launches += 2;
         // Phase 2: the reference's pinned system proper (row of the first assignable cell = identity, rhs 0).  For a consistent

@@ -1279,8 +1279,17 @@ namespace opf {
             const long long seg = it % nseg, row = it / nseg;
             const int j = r.lo[1] + (int) (row % n1), k = r.lo[2] + (int) (row / n1);
             const long long b = seg * RED_SEG, e = min(b + (long long) RED_SEG, n0);
-            for (long long ii = b + threadIdx.x; ii < e; ii += blockDim.x)
-                acc = red_comb(rop, acc, red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) ii, j, k)));
+            // four independent evaluations per trip: enough loads in flight to stream at HBM rate with 4 blocks per SM
+            long long ii = b + threadIdx.x;
+            const long long st = blockDim.x;
+            for (; ii + 3 * st < e; ii += 4 * st) {
+                const double v0 = red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) ii, j, k));
+                const double v1 = red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) (ii + st), j, k));
+                const double v2 = red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) (ii + 2 * st), j, k));
+                const double v3 = red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) (ii + 3 * st), j, k));
+                acc = red_comb(rop, red_comb(rop, red_comb(rop, red_comb(rop, acc, v0), v1), v2), v3);
+            }
+            for (; ii < e; ii += st) acc = red_comb(rop, acc, red_lift(rop, E::template eval<0, P, A0>(a, r.lo[0] + (int) ii, j, k)));
         }
         acc = block_reduce(rop, acc);
         if (threadIdx.x == 0) partials[blockIdx.x] = acc;
@@ -1353,14 +1362,22 @@ namespace opf {
         int tx = etx > 0 ? etx : 32;
         dim3 block, grid;
         int ch;
+        // march chunk: 64 steps per thread on large boxes; small boxes (coarse multigrid levels) get shorter chunks so that the
+        // grid still covers the SMs -- a thread marching 64 dependent rows alone costs ~40 us whatever the box size
+        auto pick_ch = [&](long long blocks_xy, int nmarch) {
+            int c = 64;
+            while (c > 4 && blocks_xy * ((nmarch + c - 1) / c) < 4 * 148) c >>= 1;
+            return c;
+        };
         if (DIM == 3) {
             const int ty = ety > 0 ? ety : 128 / tx;
-            ch = ech > 0 ? ech : 64;
             block = dim3(tx, ty, 1);
+            const long long bxy = (long long) ((nt + tx - 1) / tx) * ((n1 + ty - 1) / ty);
+            ch = ech > 0 ? ech : pick_ch(bxy, n2);
             grid = dim3((nt + tx - 1) / tx, (n1 + ty - 1) / ty, (n2 + ch - 1) / ch);
         } else {
             tx = etx > 0 ? etx : (nt >= 128 ? 128 : (nt >= 64 ? 64 : 32));// <= 128 (launch bounds)
-            ch = ech > 0 ? ech : 64;
+            ch = ech > 0 ? ech : pick_ch((nt + tx - 1) / tx, n1);
             block = dim3(tx, 1, 1);
             grid = dim3((nt + tx - 1) / tx, (n1 + ch - 1) / ch, 1);
         }
