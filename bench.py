@@ -253,17 +253,17 @@ def main():
     hout = torch.empty(shape[::-1], dtype=torch.float64).pin_memory()
     hin.numpy()[...] = np.ascontiguousarray(init.transpose(2, 1, 0))
     nbytes = hin.numel() * 8
+    # the public host-buffer call: opf_assign_host pipelines upload | sweep | download in z-slabs (PCIe both ways at once)
+    def e2e_step():
+        capi.check(l.opf_assign_host(u.h, capi.OP_EQ, sig.encode(), F, len(fields), S, len(scalars), u.h, C.c_void_p(hin.data_ptr()),
+                                     C.c_void_p(hout.data_ptr())))
+
     for _ in range(2):
-        u.upload_raw(hin.data_ptr(), lr)
-        u.assign(expr)
-        u.download_raw(hout.data_ptr(), lr)
+        e2e_step()
     barrier()
-    t0 = time.perf_counter()
     capi.check(l.opf_timer_begin())
     for _ in range(e2e_steps):
-        u.upload_raw(hin.data_ptr(), lr)
-        u.assign(expr)
-        u.download_raw(hout.data_ptr(), lr)
+        e2e_step()
     capi.check(l.opf_timer_end(C.byref(ms)))
     barrier()
     e2e_ms = float(ms.value)

@@ -8,6 +8,7 @@
 #include <unordered_map>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 
 namespace opfe {
 
@@ -507,6 +508,82 @@ namespace opfe {
     }
 }// namespace opfe
 
+namespace opfe {
+    // request of opf_assign_host, picked up by opf_assign_ex once the launch description is ready
+    // does updatePadding() have ghost cells to refresh (BC extension / periodic copies with a non-empty box)?
+    static bool has_ghost_fills(const opf_field_s* f) {
+        for (const auto& op : f->fill1)
+            if (op.r.count() > 0) return true;
+        for (const auto& op : f->fill2)
+            if (op.r.count() > 0) return true;
+        return false;
+    }
+    struct HostPipe {
+        opf_field_s* in_field;
+        const double* host_in;
+        double* host_out;
+        bool done;
+    };
+    static thread_local HostPipe* g_hostpipe = nullptr;
+
+    // dense host box <-> pitched field storage, asynchronous on `st`
+    static int copy_box_async(opf_field_s* f, int which, const Range& r, const double* host_base, const Range& host_box, bool to_device, cudaStream_t st) {
+        const size_t n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
+        if (n0 == 0 || n1 == 0 || n2 == 0) return OPF_OK;
+        const size_t h0 = host_box.end[0] - host_box.start[0], h1 = host_box.end[1] - host_box.start[1];
+        double* dev = f->biased(which) + ((long long) r.start[0] + (long long) r.start[1] * f->pitch1 + (long long) r.start[2] * f->pitch2);
+        double* host = const_cast<double*>(host_base) + ((size_t) (r.start[0] - host_box.start[0]) + h0 * ((size_t) (r.start[1] - host_box.start[1]) + h1 * (size_t) (r.start[2] - host_box.start[2])));
+        cudaMemcpy3DParms p = {};
+        const size_t dpitch = (f->dim >= 2 ? f->pitch1 : n0) * sizeof(double);
+        const size_t dheight = f->dim >= 3 ? (size_t) (f->pitch2 / f->pitch1) : n1;
+        cudaPitchedPtr d = make_cudaPitchedPtr(dev, dpitch, n0, dheight);
+        cudaPitchedPtr h = make_cudaPitchedPtr(host, h0 * sizeof(double), h0, h1);
+        p.srcPtr = to_device ? h : d;
+        p.dstPtr = to_device ? d : h;
+        p.extent = make_cudaExtent(n0 * sizeof(double), n1, n2);
+        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        OPF_CUDA(cudaMemcpy3DAsync(&p, st));
+        return OPF_OK;
+    }
+    // strided (cudaMemcpy3D) host<->device copies run at 32 GB/s and do not overlap with each other on this platform, dense
+    // ones at 55 GB/s per direction concurrently (measured, scratch/pcie_test.cu): PCIe moves dense slabs to/from dense staging
+    // buffers and these kernels convert between the dense slab and the pitched field storage on the device
+    __global__ void __launch_bounds__(256) slab_unpack_kernel(double* __restrict__ field, long long s1, long long s2, const double* __restrict__ dense,
+                                                              opf::LaunchRange r, long long d1, long long d2) {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= r.hi[0] - r.lo[0]) return;
+        const long long j = blockIdx.y, k = blockIdx.z;
+        field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2] = dense[x + j * d1 + k * d2];
+    }
+    __global__ void __launch_bounds__(256) slab_pack_kernel(const double* __restrict__ field, long long s1, long long s2, double* __restrict__ dense,
+                                                            opf::LaunchRange r, long long d1, long long d2) {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= r.hi[0] - r.lo[0]) return;
+        const long long j = blockIdx.y, k = blockIdx.z;
+        dense[x + j * d1 + k * d2] = field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2];
+    }
+    struct PipeStreams {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t start = nullptr, up[32] = {}, done[32] = {};
+        double *stage_in = nullptr, *stage_out = nullptr;// dense images of one field's localRange
+        long long stage_elems = 0;
+    };
+    static int pipe_streams(PipeStreams** out) {
+        static PipeStreams ps;
+        if (!ps.h2d) {
+            OPF_CUDA(cudaStreamCreateWithFlags(&ps.h2d, cudaStreamNonBlocking));
+            OPF_CUDA(cudaStreamCreateWithFlags(&ps.d2h, cudaStreamNonBlocking));
+            OPF_CUDA(cudaEventCreateWithFlags(&ps.start, cudaEventDisableTiming));
+            for (int i = 0; i < 32; ++i) {
+                OPF_CUDA(cudaEventCreateWithFlags(&ps.up[i], cudaEventDisableTiming));
+                OPF_CUDA(cudaEventCreateWithFlags(&ps.done[i], cudaEventDisableTiming));
+            }
+        }
+        *out = &ps;
+        return OPF_OK;
+    }
+}// namespace opfe
+
 using namespace opfe;
 
 // CUtensorMap factory for the TMA tile skeleton (called by the launcher templates, also from user translation units).
@@ -676,6 +753,113 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         ctx().launches++;
         return OPF_OK;
     };
+    // ---- opf_assign_host: upload | sweep | download pipelined in slabs along the slowest axis (three streams; PCIe runs in both
+    // directions at once and the sweep hides under the copies).  Fields with ghost cells to refresh after the upload, decomposed
+    // fields and 1-D fields take the sequential route in opf_assign_host.
+    if (g_hostpipe && !g_hostpipe->done) {
+        HostPipe& hp = *g_hostpipe;
+        const int ax = dst->dim - 1;
+        opf_field_s* inf = hp.in_field;
+        const int nz = dst->local.end[ax] - dst->local.start[ax];
+        const bool simple = dst->dim >= 2 && dst->neighbors.empty() && !has_ghost_fills(dst) && !has_ghost_fills(inf) && inf->neighbors.empty() && inf->local == dst->local && nz >= 16 && !(flags & OPF_ASSIGN_NO_PADDING);
+        if (simple) {
+            Context& c = ctx();
+            PipeStreams* ps;
+            if (int rc = pipe_streams(&ps)) return rc;
+            const int nch = std::min(16, nz / 8);
+            int radius = 0;// reach of the expression along the pipelined axis (planes of the next chunk a sweep needs)
+            {
+                int lo[OPF_MAX_FIELDS][D3], hi[OPF_MAX_FIELDS][D3];
+                bool used[OPF_MAX_FIELDS] = {false};
+                int z[D3] = {0, 0, 0}, mlo[D3] = {0, 0, 0}, mhi[D3] = {0, 0, 0};
+                footprint(p->tree, 0, z, z, lo, hi, used, mlo, mhi);
+                for (int k = 0; k < p->tree.nfields; ++k)
+                    if (used[k]) radius = std::max(radius, std::max(-lo[k][ax], hi[k][ax]));
+            }
+            auto zcut = [&](int cidx) { return dst->local.start[ax] + (int) ((long long) nz * cidx / nch); };
+            if (radius > zcut(1) - zcut(0)) return fail(OPF_ERR_UNSUPPORTED, "opf_assign_host: stencil reach exceeds the pipeline chunk");
+            OPF_CUDA(cudaEventRecord(ps->start, c.stream));
+            OPF_CUDA(cudaStreamWaitEvent(ps->h2d, ps->start, 0));
+            OPF_CUDA(cudaStreamWaitEvent(ps->d2h, ps->start, 0));
+            inf->bc0_clean[inf->cur] = false;
+            const long long total = dst->local.count();
+            if (total > ps->stage_elems) {
+                if (ps->stage_in) cudaFree(ps->stage_in);
+                if (ps->stage_out) cudaFree(ps->stage_out);
+                ps->stage_in = ps->stage_out = nullptr;
+                ps->stage_elems = 0;
+                OPF_CUDA(cudaMalloc(&ps->stage_in, sizeof(double) * total));
+                OPF_CUDA(cudaMalloc(&ps->stage_out, sizeof(double) * total));
+                ps->stage_elems = total;
+            }
+            // dense layout of localRange: rows of e0, planes of e0*e1 (1 in 2-D); a slab [z0, z1) of the slowest axis is contiguous
+            const long long e0 = dst->local.end[0] - dst->local.start[0], e1 = dst->dim == 3 ? dst->local.end[1] - dst->local.start[1] : 1;
+            const long long slab = e0 * e1;// doubles per index of the pipelined axis
+            auto off = [&](int zc) { return (long long) (zc - dst->local.start[ax]) * slab; };
+            auto convert = [&](opf_field_s* f, int which, double* dense, int z0, int z1, bool unpack) -> int {
+                Range r = f->local;
+                r.start[ax] = z0, r.end[ax] = z1;
+                opf::LaunchRange lr;
+                for (int d = 0; d < 3; ++d) lr.lo[d] = r.start[d], lr.hi[d] = r.end[d];
+                const dim3 grid((unsigned) ((e0 + 255) / 256), (unsigned) (r.end[1] - r.start[1]), (unsigned) (r.end[2] - r.start[2]));
+                // dense strides follow the field's axes: axis 1 stride e0; axis 2 stride e0*e1 (unused in 2-D where axis 1 is pipelined)
+                if (unpack) slab_unpack_kernel<<<grid, 256, 0, c.stream>>>(f->biased(which), f->pitch1, f->pitch2, dense + off(z0), lr, e0, e0 * e1);
+                else
+                    slab_pack_kernel<<<grid, 256, 0, c.stream>>>(f->biased(which), f->pitch1, f->pitch2, dense + off(z0), lr, e0, e0 * e1);
+                c.launches++;
+                return (int) cudaGetLastError() == 0 ? OPF_OK : fail(OPF_ERR_CUDA, "slab conversion launch failed");
+            };
+            static const bool dbg = getenv("OPF_PIPE_DEBUG") != nullptr;
+            static cudaEvent_t te[6] = {};
+            if (dbg && !te[0])
+                for (auto& e : te) cudaEventCreate(&e);
+            if (dbg) cudaEventRecord(te[0], ps->h2d);
+            for (int ci = 0; ci < nch; ++ci) {
+                OPF_CUDA(cudaMemcpyAsync(ps->stage_in + off(zcut(ci)), hp.host_in + off(zcut(ci)), sizeof(double) * (size_t) (off(zcut(ci + 1)) - off(zcut(ci))),
+                                         cudaMemcpyHostToDevice, ps->h2d));
+                OPF_CUDA(cudaEventRecord(ps->up[ci], ps->h2d));
+            }
+            if (dbg) cudaEventRecord(te[1], ps->h2d);
+            if (dbg) cudaEventRecord(te[2], c.stream);
+            const int in_buf = inf->cur;// the buffer the sweep reads (dst's `cur` flips below when dst is in_field and ping-pongs)
+            OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[0], 0));
+            if (int rc = convert(inf, in_buf, ps->stage_in, zcut(0), zcut(1), true)) return rc;
+            for (int ci = 0; ci < nch; ++ci) {
+                if (ci + 1 < nch) {// the sweep of slab ci taps the first planes of slab ci+1
+                    OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[ci + 1], 0));
+                    if (int rc = convert(inf, in_buf, ps->stage_in, zcut(ci + 1), zcut(ci + 2), true)) return rc;
+                }
+                Range box = w, clip = dst->storage;
+                box.start[ax] = std::max(w.start[ax], zcut(ci));
+                box.end[ax] = std::min(w.end[ax], zcut(ci + 1));
+                if (ci > 0) clip.start[ax] = zcut(ci);
+                if (ci < nch - 1) clip.end[ax] = zcut(ci + 1);
+                if (int rc = launch_box(box)) return rc;
+                if (ci == 0 && use_twin) dst->cur = wr;// fills and downloads address the buffer being written
+                if (int rc = field_fill_bc(dst, &clip)) return rc;
+                if (int rc = convert(dst, dst->cur, ps->stage_out, zcut(ci), zcut(ci + 1), false)) return rc;
+                OPF_CUDA(cudaEventRecord(ps->done[ci], c.stream));
+                OPF_CUDA(cudaStreamWaitEvent(ps->d2h, ps->done[ci], 0));
+                OPF_CUDA(cudaMemcpyAsync(hp.host_out + off(zcut(ci)), ps->stage_out + off(zcut(ci)), sizeof(double) * (size_t) (off(zcut(ci + 1)) - off(zcut(ci))),
+                                         cudaMemcpyDeviceToHost, ps->d2h));
+            }
+            dst->bc0_clean[dst->cur] = true;
+            if (dbg) cudaEventRecord(te[3], c.stream);
+            if (dbg) cudaEventRecord(te[4], ps->d2h);
+            OPF_CUDA(cudaStreamSynchronize(ps->d2h));
+            OPF_CUDA(cudaStreamSynchronize(c.stream));
+            if (dbg) {
+                float a = 0, b = 0, d = 0, e = 0;
+                cudaEventElapsedTime(&a, te[0], te[1]);
+                cudaEventElapsedTime(&b, te[2], te[3]);
+                cudaEventElapsedTime(&d, te[0], te[4]);
+                cudaEventElapsedTime(&e, te[0], te[3]);
+                fprintf(stderr, "[opf pipe] chunks=%d h2d %.2f ms | compute stream span %.2f ms | start->last d2h %.2f ms | start->compute end %.2f ms\n", nch, a, b, d, e);
+            }
+            hp.done = true;
+            return OPF_OK;
+        }
+    }
     // ---- slab-decomposed destination: halo exchange overlapped with the interior sweep (replaces the serial
     // pack -> MPI_Isend/Irecv -> Waitall -> unpack of CartesianField.hpp:630-768).  Order:
     //   compute stream: boundary-slab sweeps, BC fill of those planes | interior sweep, BC fill of the rest | wait(comm)
@@ -705,6 +889,29 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep
     if (flags & OPF_ASSIGN_NO_PADDING) return OPF_OK;
     return field_update_padding(dst);// CartesianField.hpp:231
+}
+
+int opf_assign_host(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
+                    int nscalars, opf_field_t in_field, const double* host_in, double* host_out) {
+    if (!dst || !in_field || !host_in || !host_out) return fail(OPF_ERR_INVALID, "null argument");
+    HostPipe hp{in_field, host_in, host_out, false};
+    g_hostpipe = &hp;
+    int rc = OPF_OK;
+    const opf_range lr_in = to_c(in_field->local), lr_out = to_c(dst->local);
+    // the pipelined route consumes the request inside opf_assign_ex; otherwise: plain upload -> assign -> download
+    const bool try_pipe = dst->dim >= 2 && dst->neighbors.empty() && !has_ghost_fills(dst) && !has_ghost_fills(in_field) && in_field->neighbors.empty() && in_field->local == dst->local
+                          && dst->local.end[dst->dim - 1] - dst->local.start[dst->dim - 1] >= 16;
+    if (!try_pipe) {
+        g_hostpipe = nullptr;
+        if ((rc = opf_field_upload(in_field, &lr_in, host_in))) return rc;
+        if ((rc = opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0))) return rc;
+        return opf_field_download(dst, &lr_out, host_out);
+    }
+    rc = opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0);
+    g_hostpipe = nullptr;
+    if (rc) return rc;
+    if (!hp.done) return fail(OPF_ERR_INVALID, "opf_assign_host: internal error, the pipelined route was not taken");
+    return OPF_OK;
 }
 
 int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src) {
