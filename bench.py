@@ -143,8 +143,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--n", type=int, default=513, help="nodes per axis (513 -> 511^3 updates per step)")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -304,10 +304,10 @@ def main():
             cores = host_cores()
             try:
                 t0 = time.time()
-                r = ref_sample(257, 6, 1, cores)
+                r = ref_sample(257, 100, 2, cores)
                 if r:
                     cpu = {"value": r["mlups"] / 1e3, "unit": "GLUPS", "cores": cores, "kind": "reference",
-                           "sample": f"reference ftcs3d 257^3 nodes, 6 steps after 1 warm-up, {cores} TBB threads, wall {time.time() - t0:.1f}s"}
+                           "sample": f"reference ftcs3d 257^3 nodes, 100 steps after 2 warm-up, {cores} TBB threads, wall {time.time() - t0:.1f}s"}
             except Exception as e:
                 cpu = {"value": None, "unit": "GLUPS", "cores": cores, "kind": "reference", "sample": f"failed: {e}"[:160]}
         line = {"metric": "grid-point updates/sec (GLUPS)", "value": glups, "unit": "GLUPS", "n_gpus": world, "steps": args.steps,

@@ -103,6 +103,7 @@ namespace opfe {
         std::vector<double> rdx, rdxh, rdxc;// Fast-mode reciprocals (opf_device.cuh AxisView)
         double* dev = nullptr;              // one allocation: x | dx | rdx | rdxh | rdxc, each n_ext long
         bool set = false;
+        bool uniform = false;// every dx entry bitwise equal (opf::AxisView::uniform)
     };
 }// namespace opfe
 

@@ -221,6 +221,8 @@ static void finish_axis(opf_mesh_s* m, int k) {
         const double dxl = (a.dx[i - 1] + a.dx[i]) * 0.5, dxr = (a.dx[i] + a.dx[i + 1]) * 0.5;
         a.rdxc[i] = 1. / ((dxl + dxr) * 0.5);
     }
+    a.uniform = !a.dx.empty();
+    for (size_t i = 1; i < a.dx.size() && a.uniform; ++i) a.uniform = a.dx[i] == a.dx[0];
     a.set = true;
     m->device_ready = false;
 }
@@ -320,8 +322,7 @@ namespace opfe {
         // single-spacing axis: every dx entry bitwise equal -> the reciprocal arrays are constant too (same formulas on the
         // same inputs; their unset end entries are never read by an in-range stencil)
         const auto& a = m->ax[d];
-        bool uni = !a.dx.empty();
-        for (size_t i = 1; i < a.dx.size() && uni; ++i) uni = a.dx[i] == a.dx[0];
+        const bool uni = a.uniform;// decided once per axis in finish_axis (a 2^26-node axis must not be rescanned per launch)
         v.uniform = uni ? 1 : 0;
         if (uni) {
             const double h = a.dx[0];

@@ -714,10 +714,10 @@ namespace opf {
         static constexpr bool ok = !overflow && (DIM == 3 || DIM == 2);
     };
 
-    template <class E, bool A0, int DIM, int CX>
+    template <class E, bool A0, int DIM, int CX, bool UNI_ = false>
     struct WinCtx {
         using WI = WinInfo<E, A0, DIM>;
-        static constexpr bool UNI = false;
+        static constexpr bool UNI = UNI_;
         const ExprArgs& a;
         int i0, j, k;
         unsigned valign;
@@ -737,7 +737,9 @@ namespace opf {
         }
         template <int D, int ARR, int O>
         __device__ __forceinline__ double coef() const {
-            if constexpr (D == 0) return cf0[ARR][O + CR];
+            if constexpr (UNI && ARR != CF_X) return a.ax[D].u[ARR];// uniform axis: constant-bank operand
+            else if constexpr (UNI) return __ldg(a.ax[D].x + ((D == 0 ? i0 : (D == 1 ? j : k)) + O));
+            else if constexpr (D == 0) return cf0[ARR][O + CR];
             else if constexpr (D == MAXIS) return cfm[ARR][O + CR];
             else return cfc[ARR][O + CR];
         }
@@ -925,11 +927,11 @@ namespace opf {
         }
     };
 
-    template <class E, class P, bool A0, int DIM, int CX, bool HASOP, int STAGES>
+    template <class E, class P, bool A0, int DIM, int CX, bool HASOP, int STAGES, bool UNI = false>
     __global__ void __launch_bounds__(128, OPF_WIN_MINBLOCKS) window_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
                                                          const double* __restrict__ oldp, const LaunchRange r, const int ch,
                                                          const int op, const unsigned valign, const int dalign, const int pd) {
-        using Ctx = WinCtx<E, A0, DIM, CX>;
+        using Ctx = WinCtx<E, A0, DIM, CX, UNI>;
         const int i0 = r.lo[0] + (blockIdx.x * blockDim.x + threadIdx.x) * CX;
         if (i0 >= r.hi[0]) return;
         Ctx c(a, valign);
@@ -948,7 +950,7 @@ namespace opf {
             c.k = 0;
         }
         const bool full = i0 + CX <= r.hi[0];
-        c.load_coefs_fixed();
+        if constexpr (!UNI) c.load_coefs_fixed();
         c.load_prologue();
         // staging ring in dynamic shared memory (STAGES > 1), private per thread
         extern __shared__ double2 opf_ring[];
@@ -985,7 +987,7 @@ namespace opf {
                 if (m + 1 < m1) c.prefetch_next();// in flight during this step's arithmetic
             }
             if (pd > 0 && m + pd < r.hi[DIM - 1]) c.prefetch_l2(pd);
-            c.load_coefs_march(m);
+            if constexpr (!UNI) c.load_coefs_march(m);
             double out[CX];
             static_for<0, CX - 1>([&](auto cc) { out[decltype(cc)::value] = E::template ev<0, P, A0, decltype(cc)::value, 0, 0>(c); });
             const long long o = (long long) i0 + (long long) c.j * dst.s1 + (long long) c.k * dst.s2;
@@ -1392,8 +1394,12 @@ namespace opf {
             return (int) cudaGetLastError();
         };
         (void) stages;// the cp.async staging ring (STAGES > 1) measured no gain over the register prefetch: not instantiated
-        if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1>, 1);
-        return go(window_kernel<E, P, A0, DIM, CX, false, 1>, 1);
+        if (li.uniform) {// single-spacing axes: coefficients from the constant bank
+            if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1, true>, 1);
+            return go(window_kernel<E, P, A0, DIM, CX, false, 1, true>, 1);
+        }
+        if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1, false>, 1);
+        return go(window_kernel<E, P, A0, DIM, CX, false, 1, false>, 1);
     }
 
     // tile shape of the TMA skeleton: each thread owns OPF_TMA_CX consecutive cells of a row, a block is (128 / OPF_TMA_CX) x OPF_TMA_BY threads

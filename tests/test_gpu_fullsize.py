@@ -1,0 +1,158 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the oracle would take minutes to hours here):
+linearity of the update map, exact stationarity of constants, conservation under periodic BCs, x<->y symmetry, EXACT-vs-FAST
+agreement, and -- for the implicit path -- the residual of the returned solution evaluated by the explicit path."""
+import numpy as np
+import pytest
+
+from opflow_b200 import capi, host
+from opflow_b200.host import (D1WENO53Downwind, D2SecondOrderCentered as D2, d2x, d2y, d2z, dx)
+
+pytestmark = pytest.mark.gpu
+
+
+def cube(n, bc_type, bcv=0.0, ext=0, name="u"):
+    mb = host.MeshBuilder(3).newMesh(n, n, n)
+    for d in range(3):
+        mb.setMeshOfDim(d, 0., 1.)
+    b = host.ExprBuilder().setName(name).setMesh(mb.build()).setExt(ext)
+    for d in range(3):
+        if bc_type == host.BCType.Periodic:
+            b.setBC(d, 0, bc_type).setBC(d, 1, bc_type)
+        else:
+            b.setBC(d, 0, bc_type, bcv).setBC(d, 1, bc_type, bcv)
+    return b.build()
+
+
+def ftcs(u, c):
+    return u + c * (d2x(D2, u) + d2y(D2, u) + d2z(D2, u))
+
+
+def separable(shape, seed):
+    rng = np.random.default_rng(seed)
+    a, b, c = (rng.standard_normal(s) for s in shape)
+    return np.asfortranarray(a[:, None, None] * b[None, :, None] * c[None, None, :])
+
+
+N = 513  # BASELINE config C2
+
+
+def test_c2_constant_is_stationary_bitwise(engine):
+    """u == BC value everywhere: every difference is exactly 0, so 5 steps leave every bit unchanged (both modes)"""
+    for mode in (capi.MODE_EXACT, capi.MODE_FAST):
+        host.set_mode(mode)
+        u = cube(N, host.BCType.Dirc, 1.0)
+        u.assign(1.0)
+        c = 0.1 / (N - 1) ** 2
+        e = ftcs(u, c)
+        for _ in range(5):
+            u.assign(e)
+        assert host.rangeReduce(u, capi.RED_MAX) == 1.0 and host.rangeReduce(u, capi.RED_MIN) == 1.0
+
+
+def test_c2_update_is_linear_and_modes_agree(engine):
+    """homogeneous Dirichlet: T(a*u1 + b*u2) == a*T(u1) + b*T(u2) to 1e-12 of the field scale after 3 steps; FAST within 1e-12 of EXACT"""
+    c = 0.1 / (N - 1) ** 2
+    res = {}
+    for mode in (capi.MODE_EXACT, capi.MODE_FAST):
+        host.set_mode(mode)
+        u = cube(N, host.BCType.Dirc, 0.0)
+        lr = u.localRange
+        f1, f2 = separable(lr.shape(3), 1), separable(lr.shape(3), 2)
+        outs = []
+        for init in (f1, f2, 0.75 * f1 - 1.5 * f2):
+            u.from_numpy(init)
+            e = ftcs(u, c)
+            for _ in range(3):
+                u.assign(e)
+            outs.append(u.to_numpy())
+        scale = max(np.abs(outs[2]).max(), 1e-300)
+        lin = np.abs(outs[2] - (0.75 * outs[0] - 1.5 * outs[1])).max() / scale
+        assert lin <= 1e-12, (mode, lin)
+        res[mode] = outs[2]
+    err = np.abs(res[capi.MODE_FAST] - res[capi.MODE_EXACT]).max() / np.abs(res[capi.MODE_EXACT]).max()
+    assert err <= 1e-12, err
+
+
+def test_c2_xy_symmetry_is_exact(engine):
+    """an initial field symmetric under x <-> y stays bitwise symmetric in EXACT mode ((d2x+d2y)+d2z commutes in its first sum)"""
+    host.set_mode(capi.MODE_EXACT)
+    u = cube(N, host.BCType.Dirc, 0.5)
+    lr = u.localRange
+    rng = np.random.default_rng(4)
+    a, c3 = rng.standard_normal(lr.shape(3)[0]), rng.standard_normal(lr.shape(3)[2])
+    init = np.asfortranarray((a[:, None, None] + a[None, :, None]) * c3[None, None, :])
+    u.from_numpy(init)
+    e = ftcs(u, 0.1 / (N - 1) ** 2)
+    for _ in range(4):
+        u.assign(e)
+    out = u.to_numpy()
+    assert np.array_equal(out, out.transpose(1, 0, 2))
+
+
+def test_periodic_box_conserves_the_sum(engine):
+    """257^3 periodic box (the C5 building block): the FTCS update conserves sum(u) to round-off"""
+    host.set_mode(capi.MODE_FAST)
+    n = 257
+    u = cube(n, host.BCType.Periodic, ext=1)
+    lr = u.localRange
+    u.from_numpy(separable(lr.shape(3), 9) + 2.0)
+    s0 = host.rangeReduce(u, capi.RED_SUM)
+    e = ftcs(u, 0.1 / (n - 1) ** 2)
+    for _ in range(10):
+        u.assign(e)
+    s1 = host.rangeReduce(u, capi.RED_SUM)
+    assert abs(s1 - s0) <= 1e-11 * abs(s0), (s0, s1)
+
+
+def test_c3_weno_full_size(engine):
+    """2^26 + 1 nodes (BASELINE config C3): a constant stays constant bitwise; FAST within 1e-11 of EXACT on the CONV1D.cpp:18 pulse"""
+    n = 2 ** 26 + 1
+    mesh = host.MeshBuilder(1).newMesh(n).setMeshOfDim(0, 0., 1.).build()
+    res = {}
+    for mode in (capi.MODE_EXACT, capi.MODE_FAST):
+        host.set_mode(mode)
+        u = host.ExprBuilder().setMesh(mesh).setName("u").setBC(0, 0, host.BCType.Dirc, 0.).setBC(0, 1, host.BCType.Dirc, 0.).setExt(3).build()
+        x = np.linspace(0., 1., n)
+        u.from_numpy(np.where((x >= 0.2) & (x <= 0.4), 1.0, 0.0))
+        e = u - (0.5 / (n - 1)) * dx(D1WENO53Downwind, u)
+        for _ in range(3):
+            u.assign(e)
+        res[mode] = u.to_numpy()
+        assert np.isfinite(res[mode]).all() and res[mode].max() <= 1.0 + 1e-9 and res[mode].min() >= -1e-9
+    assert np.abs(res[capi.MODE_FAST] - res[capi.MODE_EXACT]).max() <= 1e-11
+
+
+def test_c4_poisson_solution_satisfies_the_explicit_operator(engine):
+    """4097^2 pinned Neumann pressure problem (LidDriven2D.cpp:67-74 at BASELINE size): the solution returned by PCG+multigrid,
+    put back through the EXPLICIT operator, reproduces b to the requested tolerance -- independent of the solver's own estimate"""
+    from opflow_b200.host import EqnSolveHandler, StructSolverType as ST
+    host.set_mode(capi.MODE_FAST)
+    n = 4097
+    mesh = host.MeshBuilder(2).newMesh(n, n).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).build()
+
+    def mk(name):
+        b = host.ExprBuilder().setMesh(mesh).setName(name).setLoc([1, 1]).setExt(1)
+        for d in range(2):
+            b.setBC(d, 0, host.BCType.Neum, 0.).setBC(d, 1, host.BCType.Neum, 0.)
+        return b.build()
+
+    p, bf, pt, r = mk("p"), mk("b"), mk("pt"), mk("r")
+    sh = pt.localRange.shape(2)
+    xs = [(np.arange(sh[d]) + 0.5) / (n - 1) for d in range(2)]
+    pt.from_numpy(np.asfortranarray(np.cos(2 * np.pi * xs[0])[:, None] * np.cos(np.pi * xs[1])[None, :]))
+    lap = lambda f: d2x(D2, f) + d2y(D2, f)
+    bf.assign(lap(pt))
+    p.assign(0.0)
+    h = EqnSolveHandler(lambda e: (lap(e), bf), p, type_=ST.PCG, precond=ST.PFMG, tol=1e-10, maxIter=100, pinValue=True, staticMat=True)
+    st = h.solve()
+    assert st.relerr <= 1e-10 and st.niter <= 30, (st.niter, st.relerr)
+    r.assign(bf - lap(p))
+    bn = np.sqrt(host.rangeReduce(host.pow2(bf), capi.RED_SUM))
+    # the pinned row (first cell) is an identity row in the reference's system: exclude it from the residual norm
+    rr = r.to_numpy()
+    rr[0, 0] = 0.0
+    assert np.sqrt((rr ** 2).sum()) / bn <= 5e-10
+    # and the solution equals the manufactured one up to the pinned constant
+    diff = p.to_numpy() - pt.to_numpy()
+    diff -= diff[0, 0]
+    assert np.abs(diff).max() <= 1e-4  # b = L_h(pt) exactly, so the difference is solver-level: (rel. residual 1e-10) x (condition ~ n^2)
