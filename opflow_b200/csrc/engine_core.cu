@@ -475,7 +475,9 @@ namespace opfe {
         return true;
     }
     // launches ops[b, e) as ONE kernel
-    static int launch_fill_group(opf_field_s* f, const std::vector<FillOp>& ops, size_t b, size_t e, int lww, const Range* clip = nullptr) {
+    static int launch_fill_group(opf_field_s* f, const std::vector<FillOp>& ops, size_t b, size_t e, int lww, const Range* clip = nullptr,
+                                 cudaStream_t st = nullptr) {
+        if (!st) st = ctx().stream;
         MultiFill mf;
         mf.n = 0;
         mf.lww = lww;
@@ -490,7 +492,7 @@ namespace opfe {
         if (mf.n == 0) return OPF_OK;
         const long long total = mf.start[mf.n];
         const int blocks = (int) std::min<long long>((total + 255) / 256, 8LL * ctx().sm_count);
-        fill_kernel<<<blocks, 256, 0, ctx().stream>>>(mf);
+        fill_kernel<<<blocks, 256, 0, st>>>(mf);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
         return OPF_OK;
@@ -601,17 +603,17 @@ namespace opfe {
     }
 
     // steps 0 and 1 of updatePadding (physical boundaries), optionally restricted to a box
-    int field_fill_bc(opf_field_s* f, const Range* clip) {
+    int field_fill_bc(opf_field_s* f, const Range* clip, cudaStream_t st) {
         // step 0: all Corner-Dirichlet boundary faces in one launch (pure writes, last writer wins on shared edges)
         if (!f->fill0.empty() && !f->bc0_clean[f->cur]) {
-            if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1, clip)) return rc;
+            if (int rc = launch_fill_group(f, f->fill0, 0, f->fill0.size(), 1, clip, st)) return rc;
             if (!clip) f->bc0_clean[f->cur] = true;// a clipped caller marks the buffer itself once all its boxes are done
         }
         // step 1: one launch per axis (its two sides are independent; later axes read earlier axes' ghosts)
         for (size_t i = 0; i < f->fill1.size();) {
             size_t e = i + 1;
             while (e < f->fill1.size() && f->fill1[e].axis == f->fill1[i].axis) ++e;
-            if (int rc = launch_fill_group(f, f->fill1, i, e, 0, clip)) return rc;
+            if (int rc = launch_fill_group(f, f->fill1, i, e, 0, clip, st)) return rc;
             i = e;
         }
         return OPF_OK;
@@ -619,7 +621,7 @@ namespace opfe {
 
     int field_update_padding(opf_field_s* f) {
         if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
-        if (int rc = field_fill_bc(f, nullptr)) return rc;
+        if (int rc = field_fill_bc(f, nullptr, nullptr)) return rc;
         if (f->split_map.size() <= 1) {
             // step 2: periodic copies, one launch per axis
             for (size_t i = 0; i < f->fill2.size();) {

@@ -741,14 +741,15 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         t.org[2] = f->storage.start[2];
         if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.stride_b[0] & 15) || (t.stride_b[1] & 15) || f->dim != 3) li.tma_ok = 0;
     }
-    auto launch_box = [&](const Range& box) -> int {
+    auto launch_box = [&](const Range& box, cudaStream_t lst = nullptr) -> int {
         if (box.count() <= 0) return OPF_OK;
+        if (!lst) lst = ctx().stream;
         opf::LaunchInfo lb = li;
         for (int d = 0; d < 3; ++d) {
             lb.r.lo[d] = box.start[d];
             lb.r.hi[d] = box.end[d];
         }
-        const int rc = p->fn(&a, &lb, ctx().stream);
+        const int rc = p->fn(&a, &lb, lst);
         if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have, or its TMA descriptor could not be encoded");
         ctx().launches++;
         return OPF_OK;
@@ -862,24 +863,26 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     }
     // ---- slab-decomposed destination: halo exchange overlapped with the interior sweep (replaces the serial
     // pack -> MPI_Isend/Irecv -> Waitall -> unpack of CartesianField.hpp:630-768).  Order:
-    //   compute stream: boundary-slab sweeps, BC fill of those planes | interior sweep, BC fill of the rest | wait(comm)
-    //   comm stream   :                         wait(boundary) pack -> NCCL send/recv -> unpack
+    //   compute stream: interior sweep, BC fill of its planes ............................................ | wait(comm)
+    //   comm stream   : boundary-slab sweeps, BC fill of those planes, pack -> NCCL send/recv -> unpack
     SlabPlan sp;
     static const int overlap_on = getenv("OPF_OVERLAP") ? atoi(getenv("OPF_OVERLAP")) : 1;
     if (overlap_on && !(flags & OPF_ASSIGN_NO_PADDING) && comm_active() && slab_plan(dst, w, sp)) {
         Context& c = ctx();
-        if (int rc = launch_box(sp.lo)) return rc;
-        if (int rc = launch_box(sp.hi)) return rc;
-        if (use_twin) dst->cur = wr;
-        if (sp.has_lo)
-            if (int rc = field_fill_bc(dst, &sp.clip_lo)) return rc;
-        if (sp.has_hi)
-            if (int rc = field_fill_bc(dst, &sp.clip_hi)) return rc;
+        // the boundary slabs, their BC fills and the whole exchange run on the high-priority stream, concurrently with the
+        // interior sweep on the compute stream (disjoint planes of the destination; both read the old buffer)
         OPF_CUDA(cudaEventRecord(c.ev_compute, c.stream));
         OPF_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_compute, 0));
+        if (int rc = launch_box(sp.lo, c.comm_stream)) return rc;
+        if (int rc = launch_box(sp.hi, c.comm_stream)) return rc;
+        if (int rc = launch_box(sp.mid)) return rc;
+        if (use_twin) dst->cur = wr;
+        if (sp.has_lo)
+            if (int rc = field_fill_bc(dst, &sp.clip_lo, c.comm_stream)) return rc;
+        if (sp.has_hi)
+            if (int rc = field_fill_bc(dst, &sp.clip_hi, c.comm_stream)) return rc;
         if (int rc = halo_exchange(dst, c.comm_stream)) return rc;
         OPF_CUDA(cudaEventRecord(c.ev_comm, c.comm_stream));
-        if (int rc = launch_box(sp.mid)) return rc;
         if (int rc = field_fill_bc(dst, &sp.clip_mid)) return rc;
         dst->bc0_clean[dst->cur] = true;
         OPF_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
