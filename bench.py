@@ -133,7 +133,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "grid-point updates/sec (GLUPS)", "value": glups, "unit": "GLUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] / max(1, args.steps) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"FTCS3D heat equation {n}^3 nodes FP64 7-point explicit (reference CPU path, TBB)"},
+            "config": {"workload": f"FTCS3D heat equation {n}x{n}x{n} nodes FP64 7-point explicit, u = u + dt*alpha*(d2x+d2y+d2z)(u), Dirichlet 1",
+                       "mode": "reference CPU path (unmodified OpFlow, TBB rangeFor, all host cores)", "parallelism": "host cores only"},
             "cpu_baseline": {"value": glups, "unit": "GLUPS", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": glups, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

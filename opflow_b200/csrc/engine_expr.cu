@@ -526,25 +526,6 @@ namespace opfe {
     };
     static thread_local HostPipe* g_hostpipe = nullptr;
 
-    // dense host box <-> pitched field storage, asynchronous on `st`
-    static int copy_box_async(opf_field_s* f, int which, const Range& r, const double* host_base, const Range& host_box, bool to_device, cudaStream_t st) {
-        const size_t n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
-        if (n0 == 0 || n1 == 0 || n2 == 0) return OPF_OK;
-        const size_t h0 = host_box.end[0] - host_box.start[0], h1 = host_box.end[1] - host_box.start[1];
-        double* dev = f->biased(which) + ((long long) r.start[0] + (long long) r.start[1] * f->pitch1 + (long long) r.start[2] * f->pitch2);
-        double* host = const_cast<double*>(host_base) + ((size_t) (r.start[0] - host_box.start[0]) + h0 * ((size_t) (r.start[1] - host_box.start[1]) + h1 * (size_t) (r.start[2] - host_box.start[2])));
-        cudaMemcpy3DParms p = {};
-        const size_t dpitch = (f->dim >= 2 ? f->pitch1 : n0) * sizeof(double);
-        const size_t dheight = f->dim >= 3 ? (size_t) (f->pitch2 / f->pitch1) : n1;
-        cudaPitchedPtr d = make_cudaPitchedPtr(dev, dpitch, n0, dheight);
-        cudaPitchedPtr h = make_cudaPitchedPtr(host, h0 * sizeof(double), h0, h1);
-        p.srcPtr = to_device ? h : d;
-        p.dstPtr = to_device ? d : h;
-        p.extent = make_cudaExtent(n0 * sizeof(double), n1, n2);
-        p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-        OPF_CUDA(cudaMemcpy3DAsync(&p, st));
-        return OPF_OK;
-    }
     // strided (cudaMemcpy3D) host<->device copies run at 32 GB/s and do not overlap with each other on this platform, dense
     // ones at 55 GB/s per direction concurrently (measured, scratch/pcie_test.cu): PCIe moves dense slabs to/from dense staging
     // buffers and these kernels convert between the dense slab and the pitched field storage on the device

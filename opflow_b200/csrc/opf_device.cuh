@@ -689,27 +689,6 @@ namespace opf {
             return v;
         }
         static constexpr int XL = bound(0), XH = bound(1), CL = bound(2), CH = bound(3), ML = bound(4), MH = bound(5);
-        // per-thread staging ring (cp.async): every used column contributes CX/2 16-byte core pairs and its halo doubles
-        __host__ __device__ static constexpr int halo_count(int s, int dc) { return col_xhi(s, dc) - col_xlo(s, dc); }
-        __host__ __device__ static constexpr int col_index(int s, int dc) {// running index of used columns before (s,dc)
-            int n = 0;
-            for (int ss = 0; ss < NS; ++ss)
-                for (int d = -WR; d <= WR; ++d) {
-                    if (ss == s && d == dc) return n;
-                    if (col_used(ss, d)) ++n;
-                }
-            return n;
-        }
-        __host__ __device__ static constexpr int halo_off(int s, int dc) {
-            int n = 0;
-            for (int ss = 0; ss < NS; ++ss)
-                for (int d = -WR; d <= WR; ++d) {
-                    if (ss == s && d == dc) return n;
-                    if (col_used(ss, d)) n += halo_count(ss, d);
-                }
-            return n;
-        }
-        static constexpr int NCOLS = col_index(NS, -WR - 1), NHALO = halo_off(NS, -WR - 1);
         // cross offsets only exist in 3-D
         static constexpr bool ok = !overflow && (DIM == 3 || DIM == 2);
     };
@@ -817,81 +796,6 @@ namespace opf {
                 });
             });
         }
-        // ---- cp.async staging ring: each thread copies the leading rows of a future march step straight from global
-        // to its PRIVATE shared-memory slots (no barrier needed: a thread only ever reads what it copied itself), so the
-        // DRAM latency of STAGES-1 march steps is hidden without spending registers.  Layout (conflict-free, lanes
-        // contiguous): pairs[stage][pair][thread] as double2, then halos[stage][halo][thread] as double.
-        // colp[ci]: pointer to element x = i0 of column ci's leading row for the NEXT march index to be staged; bumped
-        // by the march stride after every issue (no 64-bit multiplies in the loop)
-        __device__ __forceinline__ void init_colp(const double** colp, int mfirst) {
-            static_for<0, WI::NS - 1>([&](auto s) {
-                static_for<WI::CL, WI::CH>([&](auto dc) {
-                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
-                    if constexpr (WI::col_used(S, DC)) {
-                        constexpr int DM = WI::col_mhi(S, DC);
-                        const FieldView& v = a.f[S];
-                        const int jj = DIM == 3 ? j + DC : mfirst + DM, kk = DIM == 3 ? mfirst + DM : 0;
-                        colp[WI::col_index(S, DC)] = v.p + ((long long) i0 + (long long) jj * v.s1 + (long long) kk * v.s2);
-                    }
-                });
-            });
-        }
-        __device__ __forceinline__ void issue_stage(const double** colp, unsigned pair_sa, unsigned halo_sa, unsigned ntb) {
-            // pair_sa / halo_sa: shared-space byte addresses of this thread's first pair / halo slot of the target stage;
-            // ntb = threads per block * 8 bytes
-            static_for<0, WI::NS - 1>([&](auto s) {
-                static_for<WI::CL, WI::CH>([&](auto dc) {
-                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
-                    if constexpr (WI::col_used(S, DC)) {
-                        constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC);
-                        constexpr int ci = WI::col_index(S, DC), ho = WI::halo_off(S, DC);
-                        const double* rp = colp[ci];
-#pragma unroll
-                        for (int c = 0; c < CX; c += 2) {
-                            const unsigned d = pair_sa + (unsigned) (ci * (CX / 2) + c / 2) * 2u * ntb;
-                            if ((valign >> S) & 1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(rp + c));
-                            else {
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(rp + c));
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d + 8u), "l"(rp + c + 1));
-                            }
-                        }
-                        int h = 0;
-#pragma unroll
-                        for (int x = xlo; x < 0; ++x, ++h)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(halo_sa + (unsigned) (ho + h) * ntb), "l"(rp + x));
-#pragma unroll
-                        for (int x = CX; x <= CX - 1 + xhi; ++x, ++h)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(halo_sa + (unsigned) (ho + h) * ntb), "l"(rp + x));
-                        colp[ci] = rp + (DIM == 3 ? a.f[S].s2 : a.f[S].s1);
-                    }
-                });
-            });
-        }
-        // staged rows -> the window's prefetch slot (march offset mhi + 1)
-        __device__ __forceinline__ void consume_stage(const double2* pairs, const double* halos, int nt) {
-            // pairs / halos: this thread's first pair / halo slot of the stage
-            static_for<0, WI::NS - 1>([&](auto s) {
-                static_for<WI::CL, WI::CH>([&](auto dc) {
-                    constexpr int S = decltype(s)::value, DC = decltype(dc)::value;
-                    if constexpr (WI::col_used(S, DC)) {
-                        constexpr int xlo = WI::col_xlo(S, DC), xhi = WI::col_xhi(S, DC), DM = WI::col_mhi(S, DC) + 1;
-                        constexpr int ci = WI::col_index(S, DC), ho = WI::halo_off(S, DC);
-                        double* row = w[S][DM - WI::ML][DC - WI::CL];
-#pragma unroll
-                        for (int c = 0; c < CX; c += 2) {
-                            const double2 t = pairs[(ci * (CX / 2) + c / 2) * nt];
-                            row[c - WI::XL] = t.x;
-                            row[c + 1 - WI::XL] = t.y;
-                        }
-                        int h = 0;
-#pragma unroll
-                        for (int x = xlo; x < 0; ++x, ++h) row[x - WI::XL] = halos[(ho + h) * nt];
-#pragma unroll
-                        for (int x = CX; x <= CX - 1 + xhi; ++x, ++h) row[x - WI::XL] = halos[(ho + h) * nt];
-                    }
-                });
-            });
-        }
         // L2 prefetch of the DRAM-unique stream: the leading row of the dc = 0 column of every slot, `pd` march steps
         // ahead (one request per 128-byte line: lanes whose tile starts a line).  Costs no registers, unlike a deeper
         // register pipeline, and turns the later vector load into an L2 hit.
@@ -927,7 +831,7 @@ namespace opf {
         }
     };
 
-    template <class E, class P, bool A0, int DIM, int CX, bool HASOP, int STAGES, bool UNI = false>
+    template <class E, class P, bool A0, int DIM, int CX, bool HASOP, bool UNI = false>
     __global__ void __launch_bounds__(128, OPF_WIN_MINBLOCKS) window_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
                                                          const double* __restrict__ oldp, const LaunchRange r, const int ch,
                                                          const int op, const unsigned valign, const int dalign, const int pd) {
@@ -952,40 +856,11 @@ namespace opf {
         const bool full = i0 + CX <= r.hi[0];
         if constexpr (!UNI) c.load_coefs_fixed();
         c.load_prologue();
-        // staging ring in dynamic shared memory (STAGES > 1), private per thread
-        extern __shared__ double2 opf_ring[];
-        using WI = typename Ctx::WI;
-        const int nt = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
-        constexpr int NPAIR = WI::NCOLS * (CX / 2) > 0 ? WI::NCOLS * (CX / 2) : 1, NHAL = WI::NHALO > 0 ? WI::NHALO : 1;
-        const double2* pairs = opf_ring + tid;                                                       // + stage * NPAIR * nt
-        const double* halos = reinterpret_cast<const double*>(opf_ring + (long long) STAGES * NPAIR * nt) + tid;// + stage * NHAL * nt
-        const unsigned pair_sa = (unsigned) __cvta_generic_to_shared(pairs), halo_sa = (unsigned) __cvta_generic_to_shared(halos);
-        const unsigned ntb = (unsigned) nt * 8u, pstride = NPAIR * 2u * ntb, hstride = NHAL * ntb;
-        const double* colp[WI::NCOLS > 0 ? WI::NCOLS : 1];
-        if constexpr (STAGES > 1) {
-            c.init_colp(colp, m0 + 1);
-#pragma unroll
-            for (int sidx = 0; sidx < STAGES - 1; ++sidx) {
-                if (m0 + 1 + sidx < m1) c.issue_stage(colp, pair_sa + sidx * pstride, halo_sa + sidx * hstride, ntb);
-                asm volatile("cp.async.commit_group;");
-            }
-        }
-        int stage = 0;// stage holding march index m + 1
         for (int m = m0; m < m1; ++m) {
             if constexpr (DIM == 3) c.k = m;
             else
                 c.j = m;
-            if constexpr (STAGES > 1) {
-                // refill the slot consumed last step with march index m + STAGES, then wait for m + 1
-                const int fill = stage == 0 ? STAGES - 1 : stage - 1;
-                if (m + STAGES < m1) c.issue_stage(colp, pair_sa + fill * pstride, halo_sa + fill * hstride, ntb);
-                asm volatile("cp.async.commit_group;");
-                asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
-                if (m + 1 < m1) c.consume_stage(pairs + (long long) stage * NPAIR * nt, halos + (long long) stage * NHAL * nt, nt);
-                stage = stage + 1 == STAGES ? 0 : stage + 1;
-            } else {
-                if (m + 1 < m1) c.prefetch_next();// in flight during this step's arithmetic
-            }
+            if (m + 1 < m1) c.prefetch_next();// in flight during this step's arithmetic
             if (pd > 0 && m + pd < r.hi[DIM - 1]) c.prefetch_l2(pd);
             if constexpr (!UNI) c.load_coefs_march(m);
             double out[CX];
@@ -1384,22 +1259,16 @@ namespace opf {
             grid = dim3((nt + tx - 1) / tx, (n1 + ch - 1) / ch, 1);
         }
         static const int pd = getenv("OPF_WPD") ? atoi(getenv("OPF_WPD")) : 8;
-        static const int stages = getenv("OPF_WST") ? atoi(getenv("OPF_WST")) : 4;
-        using WI = WinInfo<E, A0, DIM>;
-        const int nthreads = block.x * block.y;
-        auto go = [&](auto kern, int st_count) {
-            const size_t smem = st_count > 1 ? (size_t) st_count * nthreads * ((WI::NCOLS * (CX / 2) > 0 ? WI::NCOLS * (CX / 2) : 1) * 16 + (WI::NHALO > 0 ? WI::NHALO : 1) * 8) : 0;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-            kern<<<grid, block, smem, st>>>(a, li.dst, li.old, li.r, ch, li.op, li.valign, li.dalign, pd);
+        auto go = [&](auto kern) {
+            kern<<<grid, block, 0, st>>>(a, li.dst, li.old, li.r, ch, li.op, li.valign, li.dalign, pd);
             return (int) cudaGetLastError();
         };
-        (void) stages;// the cp.async staging ring (STAGES > 1) measured no gain over the register prefetch: not instantiated
         if (li.uniform) {// single-spacing axes: coefficients from the constant bank
-            if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1, true>, 1);
-            return go(window_kernel<E, P, A0, DIM, CX, false, 1, true>, 1);
+            if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, true>);
+            return go(window_kernel<E, P, A0, DIM, CX, false, true>);
         }
-        if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, 1, false>, 1);
-        return go(window_kernel<E, P, A0, DIM, CX, false, 1, false>, 1);
+        if (li.op != 0) return go(window_kernel<E, P, A0, DIM, CX, true, false>);
+        return go(window_kernel<E, P, A0, DIM, CX, false, false>);
     }
 
     // tile shape of the TMA skeleton: each thread owns OPF_TMA_CX consecutive cells of a row, a block is (128 / OPF_TMA_CX) x OPF_TMA_BY threads
