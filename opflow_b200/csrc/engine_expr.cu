@@ -730,6 +730,12 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
             lb.r.lo[d] = box.start[d];
             lb.r.hi[d] = box.end[d];
         }
+        // the 16-byte alignment flags were derived for rows starting at w.start[0]: a sub-box shifted by an odd number of cells
+        // along axis 0 (decomposition along x) must fall back to scalar loads / stores
+        if ((box.start[0] - w.start[0]) & 1) {
+            lb.valign = 0;
+            lb.dalign = 0;
+        }
         const int rc = p->fn(&a, &lb, lst);
         if (rc != 0) return fail(OPF_ERR_CUDA, "launch of '%s' failed: %s", p->sig.c_str(), rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "expression uses an axis the field does not have, or its TMA descriptor could not be encoded");
         ctx().launches++;

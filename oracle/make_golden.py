@@ -26,6 +26,7 @@ EXPLICIT = [  # (fixture name, ref_explicit arguments)
     ("weno_up_n257_s40", ["--case", "weno_up", "--n", 257, "--steps", 40, "--ghosts", 1]),
     ("upwind1_n101_s100", ["--case", "upwind1", "--n", 101, "--steps", 100, "--ghosts", 1]),
     ("weno_down_n129_sin_s30", ["--case", "weno_down", "--n", 129, "--steps", 30, "--ghosts", 1, "--init", "sin"]),
+    ("ftcs2d_mpi_n65_sin_s200", ["--case", "ftcs2d_mpi", "--n", 65, "--steps", 200, "--init", "sin", "--ghosts", 1]),
 ]
 
 

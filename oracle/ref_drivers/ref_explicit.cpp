@@ -4,7 +4,7 @@
 // examples/FTCS2D/FTCS-OMP.cpp:26 (C1), its d2z extension (C2) and examples/CONV1D/CONV1D.cpp:29-31
 // with D1WENO53Downwind/Upwind or D1FirstOrderBiasedDownwind (C3).
 //
-//   ref_explicit --case ftcs2d|ftcs3d|weno_down|weno_up|upwind1 --n N --steps S --warmup W
+//   ref_explicit --case ftcs2d|ftcs3d|ftcs2d_mpi|weno_down|weno_up|upwind1 --n N --steps S --warmup W
 //                --threads T --init zero|sin --dump path --ghosts 0|1
 #include "ref_common.hpp"
 using namespace OpFlow;
@@ -20,6 +20,7 @@ static void finish(const char* name, int n, int steps, int threads, double sec, 
 }
 
 int main(int argc, char** argv) {
+    EnvironmentGardian _env(&argc, &argv);
     std::string cs = arg(argc, argv, "--case", "ftcs2d");
     int n = atoi(arg(argc, argv, "--n", "65"));
     int steps = atoi(arg(argc, argv, "--steps", "10"));
@@ -69,6 +70,34 @@ int main(int argc, char** argv) {
         for (int i = 0; i < steps; ++i) step();
         double t1 = now();
         finish("ftcs3d", n, steps, nt, t1 - t0, (long long) (n - 2) * (n - 2) * (n - 2), u, dump, ghosts);
+    } else if (cs == "ftcs2d_mpi") {
+        // the set-up of examples/FTCS2D/FTCS-MPI.cpp:12-40: cell-centred field, ext 1, padding 1, EvenSplitStrategy over the
+        // distributed workers of the global plan (one worker here for the reference build; N GPUs for the B200 front-end)
+        using Mesh = CartesianMesh<Meta::int_<2>>;
+        using Field = CartesianField<Real, Mesh>;
+        auto mesh = MeshBuilder<Mesh>().newMesh(n, n).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).build();
+        auto info = makeParallelInfo();
+        info.threadInfo.thread_count = nt;
+        setGlobalParallelInfo(info);
+        setGlobalParallelPlan(makeParallelPlan(getGlobalParallelInfo(), ParallelIdentifier::DistributeMem | ParallelIdentifier::SharedMem));
+        std::shared_ptr<AbstractSplitStrategy<Field>> strategy = std::make_shared<EvenSplitStrategy<Field>>();
+        auto u = ExprBuilder<Field>().setName("u").setMesh(mesh)
+                         .setBC(0, DimPos::start, BCType::Dirc, 1.).setBC(0, DimPos::end, BCType::Dirc, 1.)
+                         .setBC(1, DimPos::start, BCType::Dirc, 1.).setBC(1, DimPos::end, BCType::Dirc, 1.)
+                         .setLoc(std::array {LocOnMesh::Center, LocOnMesh::Center}).setExt(1).setPadding(1)
+                         .setSplitStrategy(strategy).build();
+        if (init == "sin") u.initBy([](auto&& x) { return std::sin(PI * x[0]) * std::sin(PI * x[1]); });
+        else u = 0;
+        const Real dt = 0.1 / Math::pow2(n - 1), alpha = 1.0;
+        auto step = [&] { u = u + dt * alpha * (d2x<D2SecondOrderCentered>(u) + d2y<D2SecondOrderCentered>(u)); };
+        for (int i = 0; i < warm; ++i) step();
+        double t0 = now();
+        for (int i = 0; i < steps; ++i) step();
+        double t1 = now();
+        // every worker dumps its own block (file name gets the worker id when there are several)
+        std::string path = dump;
+        if (getWorkerCount() > 1 && !path.empty()) path += "." + std::to_string(getWorkerId());
+        finish("ftcs2d_mpi", n, steps, nt, t1 - t0, (long long) (n - 1) * (n - 1), u, path.c_str(), ghosts);
     } else if (cs == "weno_down" || cs == "weno_up" || cs == "upwind1") {
         using Mesh = CartesianMesh<Meta::int_<1>>;
         using Field = CartesianField<Real, Mesh>;

@@ -1,0 +1,2 @@
+#!/bin/bash
+python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -15
