@@ -157,7 +157,8 @@ struct opf_field_s {
     int padding = 0;
     opfe::Range local, assignable, accessible, logical, storage;
     int n_ranks = 1, rank = 0;
-    std::vector<opfe::Range> split_map;
+    std::vector<opfe::Range> split_map; // per rank, Corner fields already carry the extra end node
+    std::vector<opfe::Range> cell_split;// the strategy's own cell-centred blocks (AbstractSplitStrategy::getSplitMap), empty on one rank
     std::vector<opfe::Neighbor> neighbors;
     // storage: element with global index g lives at buf[cur][lead + (g0-S0) + (g1-S1)*pitch1 + (g2-S2)*pitch2]
     double* buf[2] = {nullptr, nullptr};
@@ -186,4 +187,5 @@ namespace opfe {
     int halo_exchange(opf_field_s* f, cudaStream_t st);// engine_comm.cu: pack, NCCL send/recv group, unpack -- all on `st`
     void compute_neighbors(opf_field_s* f);
     bool comm_active();
+    int comm_allreduce_device(double* dev, int n, int rop, cudaStream_t st);// in place, stream-ordered, no host synchronisation
 }// namespace opfe

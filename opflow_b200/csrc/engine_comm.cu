@@ -92,6 +92,14 @@ namespace {
 namespace opfe {
     bool comm_active() { return nc().comm != nullptr; }
 
+    int comm_allreduce_device(double* dev, int cnt, int rop, cudaStream_t st) {
+        Nccl& n = nc();
+        if (!n.comm || cnt <= 0) return OPF_OK;
+        const int op = rop == OPF_RED_MAX || rop == OPF_RED_ABSMAX ? ncclMax : (rop == OPF_RED_MIN ? ncclMin : ncclSum);
+        OPF_NCCL(n.AllReduce(dev, dev, (size_t) cnt, ncclFloat64, op, n.comm, st));
+        return OPF_OK;
+    }
+
     int halo_exchange(opf_field_s* f, cudaStream_t st) {
         Nccl& n = nc();
         if (f->neighbors.empty()) return OPF_OK;

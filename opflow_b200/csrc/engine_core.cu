@@ -777,6 +777,7 @@ static opf_field_s* plan_field(const opf_field_desc* desc, const char* name, boo
         // strategy->splitRange / getSplitMap on the mesh range; Corner fields take the extra end node (:1004-1022)
         f->split_map.clear();
         for (int r = 0; r < f->n_ranks; ++r) f->split_map.push_back(from_c(desc->split_map[r], dim));
+        f->cell_split = f->split_map;
         f->local = f->split_map[f->rank];
         for (int i = 0; i < dim; ++i) {
             if (f->loc[i] == OPF_LOC_CORNER && f->local.end[i] == m->range.end[i] - 1)

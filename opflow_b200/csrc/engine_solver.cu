@@ -28,8 +28,12 @@ namespace {
         double* coarse;
         long long cs1, cs2;
         int dim;
-        int flo[3], fhi[3];// fine writable range
-        int clo[3], chi[3];// coarse writable range
+        int flo[3], fhi[3];// fine writable range of the whole (global) field: validity + wall logic
+        int clo[3], chi[3];// coarse writable range of the whole (global) field
+        int wlo[3], whi[3];// the box this launch writes (this rank's part of the coarse / fine level)
+        // decomposed levels keep their periodic images in the halo (filled by the exchange): indices are then NOT wrapped, the
+        // ghost cell is read instead -- the wrapped cell may live on another rank
+        int fhalo[3], chalo[3];
         int f0[3], c0[3];  // accessible.start of fine / coarse (index origin of the 2:1 map)
         int center[3], periodic[3], fper[3], cper[3];
         int bclo[3], bchi[3];// opf_bctype of the unknown per axis side (cell-centred prolongation at the walls)
@@ -37,6 +41,10 @@ namespace {
 
     __device__ __forceinline__ bool in_box(const int* g, const int* lo, const int* hi) {
         return g[0] >= lo[0] && g[0] < hi[0] && g[1] >= lo[1] && g[1] < hi[1] && g[2] >= lo[2] && g[2] < hi[2];
+    }
+    // same, but axes flagged in `halo` accept any index (their out-of-range cells are valid periodic images in the halo)
+    __device__ __forceinline__ bool in_box_halo(const int* g, const int* lo, const int* hi, const int* halo) {
+        return (halo[0] || (g[0] >= lo[0] && g[0] < hi[0])) && (halo[1] || (g[1] >= lo[1] && g[1] < hi[1])) && (halo[2] || (g[2] >= lo[2] && g[2] < hi[2]));
     }
 
     // per-axis prolongation weight of coarse cell I for fine cell i (cell-centred axes), shared by both transfer kernels so
@@ -47,9 +55,11 @@ namespace {
         int nb = (r & 1) ? par + 1 : par - 1;
         bool wall = false;
         if (p.periodic[d]) {
-            if (nb < p.c0[d]) nb += p.cper[d];
-            else if (nb >= p.c0[d] + p.cper[d])
-                nb -= p.cper[d];
+            if (!p.chalo[d]) {
+                if (nb < p.c0[d]) nb += p.cper[d];
+                else if (nb >= p.c0[d] + p.cper[d])
+                    nb -= p.cper[d];
+            }
         } else if (nb < p.clo[d] || nb >= p.chi[d]) {
             wall = true;
         }
@@ -68,8 +78,8 @@ namespace {
         // one thread per coarse cell; rows / planes come from the grid (no 64-bit divisions), axis 0 is coalesced
         {
             const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
-            if (x0 >= p.chi[0] - p.clo[0]) return;
-            int I[3] = {p.clo[0] + x0, p.clo[1] + (int) blockIdx.y, p.clo[2] + (int) blockIdx.z};
+            if (x0 >= p.whi[0] - p.wlo[0]) return;
+            int I[3] = {p.wlo[0] + x0, p.wlo[1] + (int) blockIdx.y, p.wlo[2] + (int) blockIdx.z};
             int idx[3][4], cnt[3];
             double wgt[3][4];
             for (int d = 0; d < 3; ++d) {
@@ -79,19 +89,19 @@ namespace {
                     cnt[d] = 4;
                     for (int a = 0; a < 4; ++a) {
                         int i = p.f0[d] + 2 * (I[d] - p.c0[d]) - 1 + a;
-                        if (p.periodic[d]) {
+                        if (p.periodic[d] && !p.fhalo[d]) {
                             if (i < p.f0[d]) i += p.fper[d];
                             else if (i >= p.f0[d] + p.fper[d])
                                 i -= p.fper[d];
                         }
                         idx[d][a] = i;
-                        wgt[d][a] = (i >= p.flo[d] && i < p.fhi[d]) ? 0.5 * cc_weight(p, d, i, I[d]) : 0.0;
+                        wgt[d][a] = ((i >= p.flo[d] && i < p.fhi[d]) || (p.periodic[d] && p.fhalo[d])) ? 0.5 * cc_weight(p, d, i, I[d]) : 0.0;
                     }
                 } else {
                     cnt[d] = 3;
                     for (int a = 0; a < 3; ++a) {
                         int i = p.f0[d] + 2 * (I[d] - p.c0[d]) - 1 + a;
-                        if (p.periodic[d]) {
+                        if (p.periodic[d] && !p.fhalo[d]) {
                             if (i < p.f0[d]) i += p.fper[d];
                             else if (i >= p.f0[d] + p.fper[d])
                                 i -= p.fper[d];
@@ -107,7 +117,7 @@ namespace {
                     for (int a = 0; a < cnt[0]; ++a) {
                         const int g[3] = {idx[0][a], idx[1][b], idx[2][c]};
                         const double w = wgt[0][a] * wgt[1][b] * wgt[2][c];
-                        if (w == 0.0 || !in_box(g, p.flo, p.fhi)) continue;
+                        if (w == 0.0 || !in_box_halo(g, p.flo, p.fhi, p.fhalo)) continue;
                         acc += w * p.fine[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2];
                     }
             p.coarse[(long long) I[0] + (long long) I[1] * p.cs1 + (long long) I[2] * p.cs2] = acc;
@@ -120,8 +130,8 @@ namespace {
     __global__ void __launch_bounds__(256) prolong_kernel(const XferParams p) {
         {
             const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
-            if (x0 >= p.fhi[0] - p.flo[0]) return;
-            int g[3] = {p.flo[0] + x0, p.flo[1] + (int) blockIdx.y, p.flo[2] + (int) blockIdx.z};
+            if (x0 >= p.whi[0] - p.wlo[0]) return;
+            int g[3] = {p.wlo[0] + x0, p.wlo[1] + (int) blockIdx.y, p.wlo[2] + (int) blockIdx.z};
             int idx[3][2], cnt[3];
             double wgt[3][2];
             for (int d = 0; d < 3; ++d) {
@@ -133,7 +143,7 @@ namespace {
                 const int par = p.c0[d] + (r >> 1);
                 if (p.center[d]) {
                     int nb = (r & 1) ? par + 1 : par - 1;
-                    if (p.periodic[d]) {
+                    if (p.periodic[d] && !p.chalo[d]) {
                         if (nb < p.c0[d]) nb += p.cper[d];
                         else if (nb >= p.c0[d] + p.cper[d])
                             nb -= p.cper[d];
@@ -144,7 +154,7 @@ namespace {
                     idx[d][0] = par, cnt[d] = 1, wgt[d][0] = 1.0;
                 } else {
                     idx[d][0] = par, idx[d][1] = par + 1, cnt[d] = 2, wgt[d][0] = wgt[d][1] = 0.5;
-                    if (p.periodic[d] && idx[d][1] >= p.c0[d] + p.cper[d]) idx[d][1] -= p.cper[d];
+                    if (p.periodic[d] && !p.chalo[d] && idx[d][1] >= p.c0[d] + p.cper[d]) idx[d][1] -= p.cper[d];
                 }
             }
             double acc = 0.0;
@@ -152,7 +162,7 @@ namespace {
                 for (int b = 0; b < cnt[1]; ++b)
                     for (int a = 0; a < cnt[0]; ++a) {
                         const int I[3] = {idx[0][a], idx[1][b], idx[2][c]};
-                        if (!in_box(I, p.clo, p.chi)) continue;
+                        if (!in_box_halo(I, p.clo, p.chi, p.chalo)) continue;
                         acc += wgt[0][a] * wgt[1][b] * wgt[2][c] * p.coarse[(long long) I[0] + (long long) I[1] * p.cs1 + (long long) I[2] * p.cs2];
                     }
             p.fine[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2] += acc;
@@ -222,7 +232,10 @@ struct opf_solver_s {
     struct Level {
         opf_mesh_s* mesh = nullptr;
         opf_field_s *x = nullptr, *b = nullptr, *r = nullptr, *q = nullptr, *dinv = nullptr;
-        Range w;
+        Range w;            // cells this rank writes on this level
+        Range g;            // writable cells of the whole level (== w on one rank and on replicated levels)
+        bool dist = false;  // fields are slab/block-decomposed like the target (halo exchange in updatePadding, global reductions)
+        bool owns_pin = true;// the first assignable cell lies in w
         long long pin_off = 0;// first assignable cell of this level (pinned on every level when the problem is pinned)
     };
     opf_field_s* target = nullptr;
@@ -294,7 +307,7 @@ namespace {
             return rc;
         if (s->affine && level == 0 && !raw)
             if (int rc = assign(out, "Sub<F<0>,F<1>>", {out, s->C0}, {})) return rc;
-        if (s->pin_active && pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
+        if (s->pin_active && pin && s->lv[level].owns_pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
             copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(out->biased(out->cur), in->biased(in->cur), s->lv[level].pin_off);
             ctx().launches++;
         }
@@ -320,7 +333,8 @@ namespace {
         if (s->target->n_ranks > 1 && comm_active()) return opf_comm_allreduce(out, 1, OPF_RED_SUM);
         return OPF_OK;
     }
-    void poke(opf_field_s* f, long long off, double v) {
+    void poke(Solver* s, opf_field_s* f, long long off, double v) {// the pinned cell lives on one rank only
+        if (!s->lv[0].owns_pin) return;
         set_cell_kernel<<<1, 1, 0, ctx().stream>>>(f->biased(f->cur), off, v);
         ctx().launches++;
     }
@@ -372,8 +386,12 @@ namespace {
         XferParams p{};
         p.dim = s->target->dim;
         for (int d = 0; d < 3; ++d) {
-            p.flo[d] = Lf.w.start[d], p.fhi[d] = Lf.w.end[d];
-            p.clo[d] = Lc.w.start[d], p.chi[d] = Lc.w.end[d];
+            p.flo[d] = Lf.g.start[d], p.fhi[d] = Lf.g.end[d];
+            p.clo[d] = Lc.g.start[d], p.chi[d] = Lc.g.end[d];
+            p.wlo[d] = 0, p.whi[d] = 1;
+            const bool per = d < p.dim && Lf.x->bc[d][0].type == OPF_BC_PERIODIC;
+            p.fhalo[d] = per && Lf.dist;
+            p.chalo[d] = per && Lc.dist;
             p.f0[d] = Lf.x->accessible.start[d], p.c0[d] = Lc.x->accessible.start[d];
             p.center[d] = d < p.dim ? (Lf.x->loc[d] == OPF_LOC_CENTER || Lf.x->bc[d][0].type == OPF_BC_PERIODIC) : 0;
             p.periodic[d] = d < p.dim && Lf.x->bc[d][0].type == OPF_BC_PERIODIC;
@@ -390,10 +408,12 @@ namespace {
 
     // singular operators (the caller pinned a value: all-Neumann / periodic): keep every level's right-hand side in the
     // range of the operator by removing its mean -- on the device, no host round trip
-    int project_mean(Solver* s, opf_field_s* f, const Range& w) {
+    int project_mean(Solver* s, opf_field_s* f, const Range& w, const Range& g, bool dist) {
         double* dev = nullptr;
         if (int rc = reduce_sum_device(f, w, &dev)) return rc;
-        sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(f->biased(f->cur), f->pitch1, f->pitch2, lr_of(w), dev, 1.0 / (double) w.count());
+        if (dist)
+            if (int rc = comm_allreduce_device(dev, 1, OPF_RED_SUM, ctx().stream)) return rc;
+        sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(f->biased(f->cur), f->pitch1, f->pitch2, lr_of(w), dev, 1.0 / (double) g.count());
         ctx().launches++;
         return OPF_OK;
     }
@@ -402,7 +422,7 @@ namespace {
         auto& L = s->lv[level];
         const int last = (int) s->lv.size() - 1;
         if (s->singular)
-            if (int rc = project_mean(s, L.b, L.w)) return rc;
+            if (int rc = project_mean(s, L.b, L.w, L.g, L.dist)) return rc;
         static const int coarse_sweeps = getenv("OPF_MG_COARSE_SWEEPS") ? atoi(getenv("OPF_MG_COARSE_SWEEPS")) : 8;
         if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : coarse_sweeps, zero_guess);
         const int pre = std::max(1, s->params.num_pre_relax), post = std::max(1, s->params.num_post_relax);
@@ -410,20 +430,42 @@ namespace {
         if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
         auto& C = s->lv[level + 1];
         XferParams p = xfer(s, level);
+        // ---- restriction.  Decomposed fine level: the stencil reaches one cell into the neighbours' blocks -> refresh r's halo.
+        if (L.dist)
+            if (int rc = field_update_padding(L.r)) return rc;
         p.fine = L.r->biased(L.r->cur), p.fs1 = L.r->pitch1, p.fs2 = L.r->pitch2;
         p.coarse = C.b->biased(C.b->cur), p.cs1 = C.b->pitch1, p.cs2 = C.b->pitch2;
-        restrict_kernel<<<box_grid(C.w).grid, box_grid(C.w).block, 0, ctx().stream>>>(p);
-        ctx().launches++;
+        Range cw = C.w;
+        if (L.dist && !C.dist) {
+            // transition to the replicated coarse hierarchy: every rank restricts the coarse cells under its own fine block into a
+            // zeroed full-size coarse vector, one allreduce makes it whole on every rank
+            for (int d = 0; d < 3; ++d) {
+                cw.start[d] = std::max(C.g.start[d], C.x->accessible.start[d] + (L.w.start[d] - L.x->accessible.start[d] + 1) / 2);
+                cw.end[d] = std::min(C.g.end[d], C.x->accessible.start[d] + (L.w.end[d] - L.x->accessible.start[d] + 1) / 2);
+            }
+            OPF_CUDA(cudaMemsetAsync(C.b->buf[C.b->cur], 0, sizeof(double) * C.b->elems, ctx().stream));
+        }
+        for (int d = 0; d < 3; ++d) p.wlo[d] = cw.start[d], p.whi[d] = cw.end[d];
+        if (cw.count() > 0) {
+            restrict_kernel<<<box_grid(cw).grid, box_grid(cw).block, 0, ctx().stream>>>(p);
+            ctx().launches++;
+        }
+        if (L.dist && !C.dist)
+            if (int rc = comm_allreduce_device(C.b->buf[C.b->cur], (int) C.b->elems, OPF_RED_SUM, ctx().stream)) return rc;
         if (int rc = vcycle(s, level + 1, true)) return rc;
+        // ---- prolongation: a fine cell interpolates from its parent and the parent's neighbour -> coarse halo on decomposed levels
+        if (C.dist)
+            if (int rc = field_update_padding(C.x)) return rc;
         p.fine = L.x->biased(L.x->cur), p.fs1 = L.x->pitch1, p.fs2 = L.x->pitch2;
         p.coarse = C.x->biased(C.x->cur), p.cs1 = C.x->pitch1, p.cs2 = C.x->pitch2;
+        for (int d = 0; d < 3; ++d) p.wlo[d] = L.w.start[d], p.whi[d] = L.w.end[d];
         prolong_kernel<<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
         return smooth(s, level, post, false);
     }
 
-    int project_mean(Solver* s, opf_field_s* f, const Range& w);
+    int project_mean(Solver* s, opf_field_s* f, const Range& w, const Range& g, bool dist);
     // z = M^-1 r
     int precondition(Solver* s, opf_field_s* r, opf_field_s* z) {
         auto& L0 = s->lv[0];
@@ -438,7 +480,7 @@ namespace {
                     return assign(z, "F<0>", {L0.x}, {});
                 };
                 static const int graphs_on = getenv("OPF_GRAPHS") ? atoi(getenv("OPF_GRAPHS")) : 1;
-                if (!graphs_on) return body();
+                if (!graphs_on || s->lv[0].dist) return body();// NCCL exchanges inside: not captured
                 Solver::VGraph* g = nullptr;
                 for (auto& e : s->vgraphs)
                     if (e.r == r && e.z == z) g = &e;
@@ -481,13 +523,13 @@ namespace {
     }
     int precondition_pinned(Solver* s, opf_field_s* r, opf_field_s* z) {
         if (int rc = precondition(s, r, z)) return rc;
-        if (s->pin_active) poke(z, s->pin_off, 0.0);// keep the pinned unknown out of the Krylov space (projection P M P)
+        if (s->pin_active) poke(s, z, s->pin_off, 0.0);// keep the pinned unknown out of the Krylov space (projection P M P)
         else if (s->singular)
-            return project_mean(s, z, s->lv[0].w);// singular phase: stay in the mean-free subspace
+            return project_mean(s, z, s->lv[0].w, s->lv[0].g, s->lv[0].dist);// singular phase: stay in the mean-free subspace
         return OPF_OK;
     }
 
-    opf_field_s* make_level_field(opf_field_s* like, opf_mesh_s* mesh, const char* name) {
+    opf_field_s* make_level_field(opf_field_s* like, opf_mesh_s* mesh, const char* name, const std::vector<opf_range>* split = nullptr) {
         opf_field_desc d{};
         d.mesh = mesh;
         for (int a = 0; a < like->dim; ++a) {
@@ -501,6 +543,11 @@ namespace {
         }
         d.padding = like->padding;
         d.n_ranks = 0;
+        if (split) {// same decomposition as the target, block boundaries halved
+            d.n_ranks = like->n_ranks;
+            d.rank = like->rank;
+            d.split_map = split->data();
+        }
         return opf_field_create(&d, name);
     }
 
@@ -511,6 +558,14 @@ namespace {
         Solver::Level L0;
         L0.mesh = t->mesh;
         L0.w = common(t->assignable, t->local);
+        L0.g = t->assignable;
+        L0.dist = t->n_ranks > 1;
+        auto owns = [](const opf_field_s* f, const Range& w) {
+            for (int d = 0; d < f->dim; ++d)
+                if (f->assignable.start[d] < w.start[d] || f->assignable.start[d] >= w.end[d]) return false;
+            return true;
+        };
+        L0.owns_pin = owns(t, L0.w);
         L0.pin_off = (long long) t->assignable.start[0] + (long long) t->assignable.start[1] * t->pitch1 + (long long) t->assignable.start[2] * t->pitch2;
         L0.x = clone_homogeneous(t, "mg.x0");
         L0.b = clone_homogeneous(t, "mg.b0");
@@ -521,13 +576,15 @@ namespace {
         s->lv.push_back(L0);
         const bool want_mg = s->params.precond == OPF_SOLVER_PFMG || s->params.precond == OPF_SOLVER_SMG || s->params.type == OPF_SOLVER_PFMG
                              || s->params.type == OPF_SOLVER_SMG;
-        // multigrid needs an operator that only involves the unknown (coefficient fields are not restricted yet) and a
-        // single-rank field
+        // multigrid needs an operator that only involves the unknown (coefficient fields are not restricted yet); a decomposed
+        // target additionally needs the communicator
         bool pure = true;
         for (size_t k = 0; k < s->lhs_fields.size(); ++k)
             if (!((s->mask >> k) & 1u)) pure = false;
-        s->mg = want_mg && pure && t->n_ranks <= 1;
+        s->mg = want_mg && pure && (t->n_ranks <= 1 || (comm_active() && !t->cell_split.empty()));
         if (!s->mg) return OPF_OK;
+        // cell-centred blocks of the current distributed level (empty once the hierarchy continues replicated on every rank)
+        std::vector<Range> blocks = t->n_ranks > 1 ? t->cell_split : std::vector<Range>();
         for (;;) {
             auto& F = s->lv.back();
             opf_mesh_s* fm = F.mesh;
@@ -539,6 +596,24 @@ namespace {
                 cd[d] = (n - 1) / 2 + 1;
             }
             if (!ok || (int) s->lv.size() >= 16) break;
+            // can the next level stay decomposed?  every block boundary must be even and every coarse block thick enough for a halo
+            std::vector<opf_range> csplit;
+            bool cdist = !blocks.empty();
+            if (cdist) {
+                const int minw = std::max(2, 2 * t->padding);
+                for (const auto& b : blocks) {
+                    Range c = b;
+                    for (int d = 0; d < dim; ++d) {
+                        const int rs = b.start[d] - fm->range.start[d], re = b.end[d] - fm->range.start[d];
+                        if ((rs & 1) || (re & 1)) cdist = false;
+                        c.start[d] = fm->range.start[d] + rs / 2;
+                        c.end[d] = fm->range.start[d] + re / 2;
+                        const bool split_axis = !(b.start[d] == fm->range.start[d] && b.end[d] == fm->range.end[d] - 1);
+                        if (split_axis && c.end[d] - c.start[d] < minw) cdist = false;
+                    }
+                    csplit.push_back(to_c(c));
+                }
+            }
             opf_mesh_s* cm = opf_mesh_create(dim, cd, fm->start, fm->pad_width);
             for (int d = 0; d < dim; ++d) {
                 cm->ext_mode[d] = fm->ext_mode[d];
@@ -547,20 +622,32 @@ namespace {
                 for (int i = 0; i < cd[d]; ++i) xs[i] = fm->ax[d].x[off + 2 * i];
                 if (int rc = opf_mesh_set_coords(cm, d, xs.data(), cd[d])) return rc;
             }
+            const std::vector<opf_range>* sp = cdist ? &csplit : nullptr;
             Solver::Level C;
             C.mesh = cm;
-            C.x = make_level_field(t, cm, "mg.x");
-            C.b = make_level_field(t, cm, "mg.b");
-            C.r = make_level_field(t, cm, "mg.r");
-            C.q = make_level_field(t, cm, "mg.q");
-            C.dinv = make_level_field(t, cm, "mg.dinv");
+            C.dist = cdist;
+            C.x = make_level_field(t, cm, "mg.x", sp);
+            C.b = make_level_field(t, cm, "mg.b", sp);
+            C.r = make_level_field(t, cm, "mg.r", sp);
+            C.q = make_level_field(t, cm, "mg.q", sp);
+            C.dinv = make_level_field(t, cm, "mg.dinv", sp);
             if (!C.x || !C.b || !C.r || !C.q || !C.dinv) return OPF_ERR_CUDA;
             opf_mesh_destroy(cm);// fields hold their own references
             C.w = common(C.x->assignable, C.x->local);
+            C.g = C.x->assignable;
+            C.owns_pin = owns(C.x, C.w);
             C.pin_off = (long long) C.x->assignable.start[0] + (long long) C.x->assignable.start[1] * C.x->pitch1
                         + (long long) C.x->assignable.start[2] * C.x->pitch2;
-            if (C.w.count() <= 0) break;
+            if (C.g.count() <= 0) {
+                for (opf_field_s* f : {C.x, C.b, C.r, C.q, C.dinv}) opf_field_destroy(f);
+                break;
+            }
             s->lv.push_back(C);
+            if (cdist) {
+                blocks.clear();
+                for (const auto& c : csplit) blocks.push_back(from_c(c, dim));
+            } else
+                blocks.clear();
         }
         return OPF_OK;
     }
@@ -737,7 +824,7 @@ static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm
                 if (int rc = vcycle(s, 0, true)) return rc;
                 if (int rc = assign(s->X, "Add<F<0>,F<1>>", {s->X, L0.x}, {})) return rc;
             }
-            if (s->pin_active) poke(s->X, s->pin_off, 0.0);
+            if (s->pin_active) poke(s, s->X, s->pin_off, 0.0);
             if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
             if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
             ++iters;
@@ -810,6 +897,8 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
                 opf_field_t F[1] = {s->C0};
                 opf_range cr = to_c(w);
                 if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &cmax)) return rc;
+                if (s->lv[0].dist)
+                    if (int rc = opf_comm_allreduce(&cmax, 1, OPF_RED_MAX)) return rc;
                 s->affine = cmax != 0.0;
             }
         }
@@ -833,6 +922,11 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
             if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &a1)) return rc;
             F[0] = L0.dinv;
             if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &dmin)) return rc;// max |1/d| = 1 / min |d|
+            if (s->lv[0].dist) {
+                double v[2] = {a1, dmin};
+                if (int rc = opf_comm_allreduce(v, 2, OPF_RED_MAX)) return rc;
+                a1 = v[0], dmin = v[1];
+            }
             if (int rc = assign(L0.x, "S<0>", {}, {0.0})) return rc;
             s->singular = dmin > 0 && a1 * dmin <= 1e-8;
         }
@@ -873,16 +967,22 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     if (s->pinned && s->singular) {
         // Phase 1: the consistent singular system on the mean-free subspace (un-pinned operator, b made mean-free), whose
         // solution shifted to x[pin] = 0 IS the reference's pinned solution whenever b is in the range of the operator.
-        if (int rc = project_mean(s, s->B, w)) return rc;
+        if (int rc = project_mean(s, s->B, w, s->lv[0].g, s->lv[0].dist)) return rc;
         if (int rc = run_iteration(s, type, w, bnorm, tol, maxit, &iters, &rel)) return rc;
-        copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(s->Q->biased(s->Q->cur), s->X->biased(s->X->cur), s->pin_off);
-        sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(s->X->biased(s->X->cur), s->X->pitch1, s->X->pitch2, lr_of(w),
-                                                                         s->Q->biased(s->Q->cur) + s->pin_off, 1.0);
-        ctx().launches += 2;
+        {// x -= x[pin]: the pinned cell's value, known to its owner, reaches every rank through a one-element sum
+            double* scal = ctx().red_buf + ctx().red_cap - 1;
+            if (s->lv[0].owns_pin) copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(scal - s->pin_off, s->X->biased(s->X->cur), s->pin_off);
+            else
+                OPF_CUDA(cudaMemsetAsync(scal, 0, sizeof(double), ctx().stream));
+            if (s->lv[0].dist)
+                if (int rc = comm_allreduce_device(scal, 1, OPF_RED_SUM, ctx().stream)) return rc;
+            sub_mean_kernel<<<box_grid(w).grid, box_grid(w).block, 0, ctx().stream>>>(s->X->biased(s->X->cur), s->X->pitch1, s->X->pitch2, lr_of(w), scal, 1.0);
+            ctx().launches += 2;
+        }
         // Phase 2: the reference's pinned system proper (row of the first assignable cell = identity, rhs 0).  For a consistent
         // b it is already converged; an inconsistent b is polished with Jacobi-preconditioned iterations on the pinned operator.
         s->pin_active = true;
-        poke(s->B, s->pin_off, 0.0);
+        poke(s, s->B, s->pin_off, 0.0);
         const int saved_pre = s->params.precond;
         s->params.precond = OPF_SOLVER_JACOBI;
         const int ptype = (type == OPF_SOLVER_PCG || type == OPF_SOLVER_PFMG || type == OPF_SOLVER_SMG || type == OPF_SOLVER_JACOBI) ? OPF_SOLVER_PCG : type;
@@ -893,8 +993,8 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     }
     if (s->pinned) {
         s->pin_active = true;
-        poke(s->B, s->pin_off, 0.0);
-        poke(s->X, s->pin_off, 0.0);
+        poke(s, s->B, s->pin_off, 0.0);
+        poke(s, s->X, s->pin_off, 0.0);
     }
     int rc = run_iteration(s, type, w, bnorm, tol, maxit, &iters, &rel);
     s->pin_active = false;
