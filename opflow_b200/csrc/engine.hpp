@@ -183,6 +183,7 @@ struct opf_field_s {
 namespace opfe {
     int field_update_padding(opf_field_s* f);
     int field_fill_bc(opf_field_s* f, const Range* clip, cudaStream_t st = nullptr);// steps 0-1 of updatePadding, optionally clipped to a box
+    int field_fill_periodic(opf_field_s* f);// step 2 local part: periodic copies of the axes that are not split across ranks
     int field_ensure_twin(opf_field_s* f);
     int halo_exchange(opf_field_s* f, cudaStream_t st);// engine_comm.cu: pack, NCCL send/recv group, unpack -- all on `st`
     void compute_neighbors(opf_field_s* f);

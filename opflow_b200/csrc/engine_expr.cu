@@ -873,7 +873,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         if (int rc = field_fill_bc(dst, &sp.clip_mid)) return rc;
         dst->bc0_clean[dst->cur] = true;
         OPF_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
-        return OPF_OK;
+        return field_fill_periodic(dst);// unsplit periodic axes: local copies over the whole logical box, exchanged planes included
     }
     if (int rc = launch_box(w)) return rc;
     if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep
