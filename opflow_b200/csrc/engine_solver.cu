@@ -239,7 +239,9 @@ struct opf_solver_s {
         long long pin_off = 0;// first assignable cell of this level (pinned on every level when the problem is pinned)
     };
     opf_field_s* target = nullptr;
-    std::string lhs_sig, res_sig;
+    std::string lhs_sig, res_sig, smooth_sig;
+    bool has_smooth_sig = false;
+    std::vector<int> smooth_coef_leaf;
     std::vector<opf_field_s*> lhs_fields;
     std::vector<double> lhs_scalars;
     unsigned mask = 0;
@@ -255,6 +257,8 @@ struct opf_solver_s {
     // decision inside: after a warm-up call it is captured once per (r, z) pair into a CUDA graph and replayed
     struct VGraph {
         opf_field_s *r, *z;
+        unsigned parity;// bit l: which buffer of level l's iterate is current (the fused sweep ping-pongs it)
+        unsigned parity_after;// the same after the V-cycle: a replay must flip the host-side `cur` flags like the captured run did
         cudaGraphExec_t exec;
         long long launches;
         int calls;
@@ -373,6 +377,17 @@ namespace {
         for (int it = 0; it < sweeps; ++it) {
             if (it == 0 && zero_guess) {
                 if (int rc = assign(L.x, "Mul<S<0>,Mul<F<0>,F<1>>>", {L.dinv, L.b}, {s->omega})) return rc;
+            } else if (s->has_smooth_sig && !s->affine) {
+                // one sweep, one pass: reads x (stencil), dinv, b; writes the twin of x (ping-pong) -- 32 B per cell instead of 56
+                if (int rc = field_update_padding(L.x)) return rc;
+                opf_field_t F[OPF_MAX_FIELDS];
+                double S[OPF_MAX_SCALARS];
+                const int nc = (int) s->smooth_coef_leaf.size(), ns = (int) s->lhs_scalars.size();
+                F[0] = L.x, F[1] = L.dinv, F[2] = L.b;
+                for (int k = 0; k < nc; ++k) F[k + 3] = s->lhs_fields[s->smooth_coef_leaf[k]];
+                S[0] = s->omega;
+                for (int k = 0; k < ns; ++k) S[k + 1] = s->lhs_scalars[k];
+                if (int rc = opf_assign_ex(L.x, OPF_OP_EQ, s->smooth_sig.c_str(), F, nc + 3, S, ns + 1, OPF_ASSIGN_NO_PADDING)) return rc;
             } else {
                 if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
                 if (int rc = assign(L.x, "Add<F<0>,Mul<S<0>,Mul<F<1>,F<2>>>>", {L.x, L.dinv, L.r}, {s->omega})) return rc;
@@ -418,10 +433,12 @@ namespace {
         return OPF_OK;
     }
 
-    int vcycle(Solver* s, int level, bool zero_guess) {
+    // top_is_mean_free: the caller guarantees a mean-free right-hand side on this level (the Krylov residual of the singular
+    // phase) -- its projection pass is skipped
+    int vcycle(Solver* s, int level, bool zero_guess, bool top_is_mean_free = false) {
         auto& L = s->lv[level];
         const int last = (int) s->lv.size() - 1;
-        if (s->singular)
+        if (s->singular && !top_is_mean_free)
             if (int rc = project_mean(s, L.b, L.w, L.g, L.dist)) return rc;
         static const int coarse_sweeps = getenv("OPF_MG_COARSE_SWEEPS") ? atoi(getenv("OPF_MG_COARSE_SWEEPS")) : 8;
         if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : coarse_sweeps, zero_guess);
@@ -473,25 +490,41 @@ namespace {
             case OPF_SOLVER_PFMG:
             case OPF_SOLVER_SMG: {
                 auto body = [&]() -> int {
-                    if (int rc = assign(L0.b, "F<0>", {r}, {})) return rc;
+                    // the V-cycle runs directly on the Krylov vectors: r is its level-0 right-hand side (read only: in the singular
+                    // phase it is mean-free already, so the level-0 projection is skipped), z its level-0 iterate -- no copies
+                    opf_field_s *sb = L0.b, *sx = L0.x;
+                    L0.b = r, L0.x = z;
                     const int cycles = std::max(1, s->params.precond_max_iter);
-                    for (int c = 0; c < cycles; ++c)
-                        if (int rc = vcycle(s, 0, c == 0)) return rc;
-                    return assign(z, "F<0>", {L0.x}, {});
+                    int rc = OPF_OK;
+                    for (int c = 0; c < cycles && !rc; ++c) rc = vcycle(s, 0, c == 0, s->singular && !s->pin_active);
+                    L0.b = sb, L0.x = sx;
+                    return rc;
                 };
                 static const int graphs_on = getenv("OPF_GRAPHS") ? atoi(getenv("OPF_GRAPHS")) : 1;
                 if (!graphs_on || s->lv[0].dist) return body();// NCCL exchanges inside: not captured
+                unsigned parity = (unsigned) z->cur;
+                for (size_t lv = 1; lv < s->lv.size(); ++lv) parity |= (unsigned) s->lv[lv].x->cur << lv;
                 Solver::VGraph* g = nullptr;
                 for (auto& e : s->vgraphs)
-                    if (e.r == r && e.z == z) g = &e;
+                    if (e.r == r && e.z == z && e.parity == parity) g = &e;
                 if (!g) {
-                    s->vgraphs.push_back(Solver::VGraph{r, z, nullptr, 0, 0});
+                    s->vgraphs.push_back(Solver::VGraph{r, z, parity, parity, nullptr, 0, 0});
                     g = &s->vgraphs.back();
                 }
                 Context& c = ctx();
+                auto current_parity = [&]() {
+                    unsigned pp = (unsigned) z->cur;
+                    for (size_t lv = 1; lv < s->lv.size(); ++lv) pp |= (unsigned) s->lv[lv].x->cur << lv;
+                    return pp;
+                };
+                auto apply_parity = [&](unsigned pp) {
+                    z->cur = (int) (pp & 1u);
+                    for (size_t lv = 1; lv < s->lv.size(); ++lv) s->lv[lv].x->cur = (int) ((pp >> lv) & 1u);
+                };
                 if (g->exec) {
                     OPF_CUDA(cudaGraphLaunch(g->exec, c.stream));
                     c.launches += g->launches;
+                    apply_parity(g->parity_after);
                     return OPF_OK;
                 }
                 if (++g->calls < 2) return body();// first call: allocations, kernel attribute set-up, BC-clean flags settle
@@ -507,6 +540,8 @@ namespace {
                 if (ce != cudaSuccess || !graph) return fail(OPF_ERR_CUDA, "V-cycle graph capture failed: %s", cudaGetErrorString(ce));
                 g->launches = c.launches - l0;
                 c.launches = l0;
+                g->parity_after = current_parity();
+                apply_parity(g->parity);// the capture recorded the launches without running them: state is still the entry state
                 const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ie != cudaSuccess) {
@@ -515,6 +550,7 @@ namespace {
                 }
                 OPF_CUDA(cudaGraphLaunch(g->exec, c.stream));
                 c.launches += g->launches;
+                apply_parity(g->parity_after);
                 return OPF_OK;
             }
             case OPF_SOLVER_JACOBI: return assign(z, "Mul<F<0>,F<1>>", {L0.dinv, r}, {});
@@ -524,8 +560,12 @@ namespace {
     int precondition_pinned(Solver* s, opf_field_s* r, opf_field_s* z) {
         if (int rc = precondition(s, r, z)) return rc;
         if (s->pin_active) poke(s, z, s->pin_off, 0.0);// keep the pinned unknown out of the Krylov space (projection P M P)
-        else if (s->singular)
-            return project_mean(s, z, s->lv[0].w, s->lv[0].g, s->lv[0].dist);// singular phase: stay in the mean-free subspace
+        else if (s->singular) {
+            // singular phase: a constant component of z is invisible to the iteration (r and A.p are mean-free, A annihilates
+            // constants) and is removed from x by the pin shift at the end -- the projection pass is only kept as an option
+            static const int project_z = getenv("OPF_MG_PROJECT_Z") ? atoi(getenv("OPF_MG_PROJECT_Z")) : 0;
+            if (project_z) return project_mean(s, z, s->lv[0].w, s->lv[0].g, s->lv[0].dist);
+        }
         return OPF_OK;
     }
 
@@ -708,6 +748,35 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
         }
         s->res_sig = "Sub<F<0>," + sh + ">";
         s->has_res_sig = opf_expr_is_registered(s->res_sig.c_str()) != 0;
+        // fused weighted-Jacobi sweep  x <- x + w * dinv * (b - lhs(x)).  Leaves: F<0> = x (every unknown leaf of lhs maps to it, so
+        // the kernel stages x once), F<1> = dinv, F<2> = b, coefficient fields of lhs follow from F<3>; S<0> = w, lhs scalars from S<1>
+        std::string sm;
+        std::vector<int> coef_leaf;// lhs leaf index of every coefficient field, in order of first appearance
+        for (size_t i = 0; i < g.size(); ++i) {
+            const bool leaf = (g[i] == 'F' || g[i] == 'S') && i + 1 < g.size() && g[i + 1] == '<' && (i == 0 || !isalnum((unsigned char) g[i - 1]));
+            if (!leaf) {
+                if (g[i] != ' ') sm.push_back(g[i]);
+                continue;
+            }
+            size_t j = i + 2;
+            int v = 0;
+            while (j < g.size() && isdigit((unsigned char) g[j])) v = v * 10 + (g[j++] - '0');
+            if (g[i] == 'S') sm += "S<" + std::to_string(v + 1);
+            else if ((unknown_mask >> v) & 1u)
+                sm += "F<0";
+            else {
+                size_t pos = 0;
+                while (pos < coef_leaf.size() && coef_leaf[pos] != v) ++pos;
+                if (pos == coef_leaf.size()) coef_leaf.push_back(v);
+                sm += "F<" + std::to_string(3 + (int) pos);
+            }
+            i = j - 1;
+        }
+        s->smooth_coef_leaf = coef_leaf;
+        s->smooth_sig = "Add<F<0>,Mul<S<0>,Mul<F<1>,Sub<F<2>," + sm + ">>>>";
+        static const int fused_on = getenv("OPF_MG_FUSED") ? atoi(getenv("OPF_MG_FUSED")) : 1;
+        s->has_smooth_sig = fused_on && (int) coef_leaf.size() + 3 <= OPF_MAX_FIELDS && n_lhs_scalars + 1 <= OPF_MAX_SCALARS
+                            && opf_expr_is_registered(s->smooth_sig.c_str()) != 0;
     }
     const Range w = common(target->assignable, target->local);
     s->pinned = params->pin_value != 0;
