@@ -527,7 +527,7 @@ namespace opfe {
     static thread_local HostPipe* g_hostpipe = nullptr;
 
     // strided (cudaMemcpy3D) host<->device copies run at 32 GB/s and do not overlap with each other on this platform, dense
-    // ones at 55 GB/s per direction concurrently (measured, scratch/pcie_test.cu): PCIe moves dense slabs to/from dense staging
+    // ones at 55 GB/s per direction concurrently (measured, tools/pcie_test.cu): PCIe moves dense slabs to/from dense staging
     // buffers and these kernels convert between the dense slab and the pitched field storage on the device
     __global__ void __launch_bounds__(256) slab_unpack_kernel(double* __restrict__ field, long long s1, long long s2, const double* __restrict__ dense,
                                                               opf::LaunchRange r, long long d1, long long d2) {
