@@ -86,6 +86,8 @@ namespace opfe {
         int red_cap = 0;
         double* red_host = nullptr;// pinned
         int sm_count = 148;
+        double* stage = nullptr;// dense staging box of opf_field_upload / download (grow-only)
+        long long stage_elems = 0;
     };
     Context& ctx();
     int fail(int code, const char* fmt, ...);
@@ -185,6 +187,8 @@ namespace opfe {
     int field_fill_bc(opf_field_s* f, const Range* clip, cudaStream_t st = nullptr);// steps 0-1 of updatePadding, optionally clipped to a box
     int field_fill_periodic(opf_field_s* f);// step 2 local part: periodic copies of the axes that are not split across ranks
     int field_ensure_twin(opf_field_s* f);
+    // dense box (strides 1, d1, d2) <-> pitched storage of buffer `which` over range r, on stream st
+    int dense_convert(opf_field_s* f, int which, double* dense, const Range& r, long long d1, long long d2, bool unpack, cudaStream_t st);
     int halo_exchange(opf_field_s* f, cudaStream_t st);// engine_comm.cu: pack, NCCL send/recv group, unpack -- all on `st`
     void compute_neighbors(opf_field_s* f);
     bool comm_active();

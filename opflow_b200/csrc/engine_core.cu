@@ -93,6 +93,7 @@ int opf_finalize(void) {
     cudaStreamSynchronize(c.stream);
     cudaFree(c.red_buf);
     cudaFreeHost(c.red_host);
+    if (c.stage) cudaFree(c.stage);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
     cudaEventDestroy(c.ev_comm);
@@ -932,11 +933,70 @@ int opf_field_device_ptr(opf_field_t f, double** first, long long* pitch1, long 
     return OPF_OK;
 }
 
+}// extern "C"
+
+// strided (cudaMemcpy3D) host<->device copies run at 32 GB/s and do not overlap with each other on this platform, dense ones at
+// 55 GB/s per direction concurrently (measured, tools/pcie_test.cu): PCIe moves dense boxes to/from a dense staging buffer and these
+// kernels convert between the dense box and the pitched field storage on the device (K6-style box copies, rows from the grid)
+namespace {
+    __global__ void __launch_bounds__(256) box_unpack_kernel(double* __restrict__ field, long long s1, long long s2, const double* __restrict__ dense,
+                                                             opf::LaunchRange r, long long d1, long long d2) {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= r.hi[0] - r.lo[0]) return;
+        const long long j = blockIdx.y, k = blockIdx.z;
+        field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2] = dense[x + j * d1 + k * d2];
+    }
+    __global__ void __launch_bounds__(256) box_pack_kernel(const double* __restrict__ field, long long s1, long long s2, double* __restrict__ dense,
+                                                           opf::LaunchRange r, long long d1, long long d2) {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= r.hi[0] - r.lo[0]) return;
+        const long long j = blockIdx.y, k = blockIdx.z;
+        dense[x + j * d1 + k * d2] = field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2];
+    }
+}// namespace
+namespace opfe {
+    int dense_convert(opf_field_s* f, int which, double* dense, const Range& r, long long d1, long long d2, bool unpack, cudaStream_t st) {
+        const int n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
+        if (n0 <= 0 || n1 <= 0 || n2 <= 0) return OPF_OK;
+        opf::LaunchRange lr;
+        for (int d = 0; d < 3; ++d) lr.lo[d] = r.start[d], lr.hi[d] = r.end[d];
+        const dim3 grid((unsigned) ((n0 + 255) / 256), (unsigned) n1, (unsigned) n2);
+        if (unpack) box_unpack_kernel<<<grid, 256, 0, st>>>(f->biased(which), f->pitch1, f->pitch2, dense, lr, d1, d2);
+        else
+            box_pack_kernel<<<grid, 256, 0, st>>>(f->biased(which), f->pitch1, f->pitch2, dense, lr, d1, d2);
+        ctx().launches++;
+        OPF_CUDA(cudaGetLastError());
+        return OPF_OK;
+    }
+}// namespace opfe
+
+extern "C" {
+
 static int copy_box(opf_field_s* f, const Range& r, double* host, bool to_device) {
     if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
     if (to_device) f->bc0_clean[f->cur] = false;
     if (!common(r, f->storage).covers(r) || r.count() <= 0) return fail(OPF_ERR_RANGE, "transfer range outside the storage of field '%s'", f->name.c_str());
     const size_t n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1], n2 = r.end[2] - r.start[2];
+    if (f->dim >= 2 && r.count() >= (1LL << 20) && n1 <= 65535 && n2 <= 65535) {
+        // large box: dense PCIe copy + on-device (un)packing instead of a strided DMA
+        Context& c = ctx();
+        const long long cnt = r.count();
+        if (cnt > c.stage_elems) {
+            if (c.stage) cudaFree(c.stage);
+            c.stage = nullptr;
+            c.stage_elems = 0;
+            OPF_CUDA(cudaMalloc(&c.stage, sizeof(double) * cnt));
+            c.stage_elems = cnt;
+        }
+        if (to_device) {
+            OPF_CUDA(cudaMemcpyAsync(c.stage, host, sizeof(double) * cnt, cudaMemcpyHostToDevice, c.stream));
+            return dense_convert(f, f->cur, c.stage, r, (long long) n0, (long long) (n0 * n1), true, c.stream);
+        }
+        if (int rc = dense_convert(f, f->cur, c.stage, r, (long long) n0, (long long) (n0 * n1), false, c.stream)) return rc;
+        OPF_CUDA(cudaMemcpyAsync(host, c.stage, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c.stream));
+        OPF_CUDA(cudaStreamSynchronize(c.stream));
+        return OPF_OK;
+    }
     double* dev = f->biased(f->cur) + ((long long) r.start[0] + (long long) r.start[1] * f->pitch1 + (long long) r.start[2] * f->pitch2);
     cudaMemcpy3DParms p = {};
     const size_t dpitch = (f->dim >= 2 ? f->pitch1 : n0) * sizeof(double);

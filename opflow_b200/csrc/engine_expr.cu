@@ -526,23 +526,6 @@ namespace opfe {
     };
     static thread_local HostPipe* g_hostpipe = nullptr;
 
-    // strided (cudaMemcpy3D) host<->device copies run at 32 GB/s and do not overlap with each other on this platform, dense
-    // ones at 55 GB/s per direction concurrently (measured, tools/pcie_test.cu): PCIe moves dense slabs to/from dense staging
-    // buffers and these kernels convert between the dense slab and the pitched field storage on the device
-    __global__ void __launch_bounds__(256) slab_unpack_kernel(double* __restrict__ field, long long s1, long long s2, const double* __restrict__ dense,
-                                                              opf::LaunchRange r, long long d1, long long d2) {
-        const int x = blockIdx.x * blockDim.x + threadIdx.x;
-        if (x >= r.hi[0] - r.lo[0]) return;
-        const long long j = blockIdx.y, k = blockIdx.z;
-        field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2] = dense[x + j * d1 + k * d2];
-    }
-    __global__ void __launch_bounds__(256) slab_pack_kernel(const double* __restrict__ field, long long s1, long long s2, double* __restrict__ dense,
-                                                            opf::LaunchRange r, long long d1, long long d2) {
-        const int x = blockIdx.x * blockDim.x + threadIdx.x;
-        if (x >= r.hi[0] - r.lo[0]) return;
-        const long long j = blockIdx.y, k = blockIdx.z;
-        dense[x + j * d1 + k * d2] = field[(r.lo[0] + x) + (r.lo[1] + j) * s1 + (r.lo[2] + k) * s2];
-    }
     struct PipeStreams {
         cudaStream_t h2d = nullptr, d2h = nullptr;
         cudaEvent_t start = nullptr, up[32] = {}, done[32] = {};
@@ -787,20 +770,13 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
             auto convert = [&](opf_field_s* f, int which, double* dense, int z0, int z1, bool unpack) -> int {
                 Range r = f->local;
                 r.start[ax] = z0, r.end[ax] = z1;
-                opf::LaunchRange lr;
-                for (int d = 0; d < 3; ++d) lr.lo[d] = r.start[d], lr.hi[d] = r.end[d];
-                const dim3 grid((unsigned) ((e0 + 255) / 256), (unsigned) (r.end[1] - r.start[1]), (unsigned) (r.end[2] - r.start[2]));
                 // dense strides follow the field's axes: axis 1 stride e0; axis 2 stride e0*e1 (unused in 2-D where axis 1 is pipelined)
-                if (unpack) slab_unpack_kernel<<<grid, 256, 0, c.stream>>>(f->biased(which), f->pitch1, f->pitch2, dense + off(z0), lr, e0, e0 * e1);
-                else
-                    slab_pack_kernel<<<grid, 256, 0, c.stream>>>(f->biased(which), f->pitch1, f->pitch2, dense + off(z0), lr, e0, e0 * e1);
-                c.launches++;
-                return (int) cudaGetLastError() == 0 ? OPF_OK : fail(OPF_ERR_CUDA, "slab conversion launch failed");
+                return dense_convert(f, which, dense + off(z0), r, e0, e0 * e1, unpack, c.stream);
             };
             static const bool dbg = getenv("OPF_PIPE_DEBUG") != nullptr;
             static cudaEvent_t te[6] = {};
             if (dbg && !te[0])
-                for (auto& e : te) cudaEventCreate(&e);
+                for (auto& ev : te) cudaEventCreate(&ev);
             if (dbg) cudaEventRecord(te[0], ps->h2d);
             for (int ci = 0; ci < nch; ++ci) {
                 OPF_CUDA(cudaMemcpyAsync(ps->stage_in + off(zcut(ci)), hp.host_in + off(zcut(ci)), sizeof(double) * (size_t) (off(zcut(ci + 1)) - off(zcut(ci))),

@@ -4,13 +4,18 @@
 // symbolic StencilField, pushes every matrix row into a HYPRE Struct matrix through host SetValues calls and re-creates /
 // re-sets-up the HYPRE solver on every solve().  Here nothing is assembled: the operator of  lhs(e) == rhs  is applied by
 // running the *same device functor* the explicit path uses, on a work vector whose ghost cells are filled with the
-// target's boundary conditions made homogeneous (A.p = lhs(G_h(p))), and b = rhs - lhs(G(0)) carries the boundary data.
+// target's boundary conditions made homogeneous (A.p = lhs(G_h(p)) - lhs(G_h(0))), and b = rhs - lhs(G(0)) carries the
+// boundary data and any unknown-free terms of lhs.
 // Krylov: PCG (HYPRE_StructPCG*, StructSolverPCG.hpp:25-96) and BiCGSTAB (StructSolverBiCGSTAB.hpp) -- the latter also
-// serves GMRES requests.  Preconditioner / stand-alone solver: geometric multigrid V-cycle (PFMG's role,
-// StructSolverPFMG.hpp:36-110) with weighted-Jacobi relaxation, full coarsening, operators re-discretised on the coarse
-// meshes by the same functor, full-weighting / averaging restriction and linear / constant prolongation chosen per axis
-// from the unknown's LocOnMesh; or plain Jacobi (StructSolverJacobi.hpp).  Dot products: warp-shuffle reductions (+ NCCL
-// allreduce when the field is decomposed).
+// serves GMRES-family requests.  Preconditioner / stand-alone solver: geometric multigrid V-cycle (PFMG's role,
+// StructSolverPFMG.hpp:36-110) with weighted-Jacobi relaxation (one fused kernel per sweep where the expression
+// x + w*dinv*(b - lhs(x)) is compiled in), full coarsening, operators re-discretised on the coarse meshes by the same
+// functor, transfer operators with R = (1/2) P^T per axis (node- or cell-centred per LocOnMesh), mean projection on singular
+// levels; or plain Jacobi (StructSolverJacobi.hpp).  The V-cycle runs directly on the Krylov vectors and is replayed as a
+// CUDA graph (keyed by the ping-pong state of the level iterates).
+// Decomposed targets: every level keeps the target's block decomposition (boundaries halved, halo exchange inside
+// updatePadding, NCCL allreduce for dot products / projections, the pinned cell handled by its owner) until blocks get
+// thinner than two halos; below that the hierarchy continues replicated on every rank behind one allreduce.
 #include "engine.hpp"
 #include <algorithm>
 #include <cmath>

@@ -9,7 +9,12 @@
 //   Exact -- IEEE-rn add/sub/mul/div intrinsics in exactly the reference's operation order (no FMA contraction):
 //            bit-identical to the reference's g++ -O3 x86-64 CPU path.
 //   Fast  -- divides by mesh spacings become multiplies by per-axis reciprocal arrays, FMA contraction allowed
-//            (<= 1e-12 relative vs the reference).
+//            (<= 1e-12 relative vs the reference).  On single-spacing axes (AxisView::uniform) the coefficients are kernel-
+//            parameter constants: no coefficient loads at all (the UNI variants of the window and TMA skeletons).
+//
+// Skeletons (K1 of SURVEY 2.3): assign_kernel (one thread per cell; 1-D and small / unaligned boxes), window_kernel
+// (per-thread register window marching the slow axis; 2-D), tma_kernel (TMA-streamed tile-plus-halo planes in a shared-memory
+// ring, own cells by LDS.128, z-planes rotated in registers; 3-D).  launcher<E, DIMS> dispatches between them.
 #pragma once
 #include <cstdint>
 #include <cuda.h>

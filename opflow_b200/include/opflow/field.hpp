@@ -514,6 +514,7 @@ namespace OpFlow {
         // CartesianField.hpp:283-294: arbitrary host functor of the physical coordinates (x, or x + dx/2 on Center axes)
         CartesianField& initBy(const std::function<D(const std::array<Real, dim>&)>& f) {
             requireInit("initBy");
+            syncToDevice();// pending host writes (operator[]) reach the device before it is overwritten, never after
             const auto w = DS::commonRange(assignableRange, localRange);
             if (w.count() > 0) {
                 std::vector<Real> vals((std::size_t) w.count());

@@ -1,0 +1,83 @@
+// tests/frontend/fe_hostaccess.cpp -- front-end semantics around the host mirror of a device field, written against the
+// reference's spellings (it also compiles against the reference): host lambdas in rangeFor / rangeReduce reading and writing
+// fields through operator[] (test/Core/Loops/RangeForTest.cpp:131-175 style), deep-copy semantics of field copies
+// (CartesianField.hpp:57-68), constant and compound assignment, and the visibility of host writes to later device sweeps.
+#include <OpFlow>
+#include <cmath>
+#include <cstdio>
+using namespace OpFlow;
+
+static int failures = 0;
+#define CHECK(cond)                                                                                                    \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #cond);                                                 \
+            ++failures;                                                                                                \
+        }                                                                                                              \
+    } while (0)
+
+int main() {
+    using Mesh = CartesianMesh<Meta::int_<2>>;
+    using Field = CartesianField<Real, Mesh>;
+    constexpr int n = 33;
+    auto mesh = MeshBuilder<Mesh>().newMesh(n, n).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 2.).build();
+    auto builder = ExprBuilder<Field>().setMesh(mesh).setExt(1).setLoc({LocOnMesh::Center, LocOnMesh::Center});
+    for (int d = 0; d < 2; ++d) builder.setBC(d, DimPos::start, BCType::Neum, 0.).setBC(d, DimPos::end, BCType::Neum, 0.);
+    auto u = builder.setName("u").build();
+    auto v = u;// deep copy
+    v.name = "v";
+    CHECK(u.assignableRange.count() == (n - 1) * (n - 1));
+
+    // 1. host writes through operator[] become visible to device sweeps
+    rangeFor(u.assignableRange, [&](auto&& i) { u[i] = 1.0 + i[0] + 100.0 * i[1]; });
+    u.updatePadding();
+    v = u * 2.0 + 1.0;// device
+    double worst = 0;
+    rangeFor_s(v.assignableRange, [&](auto&& i) { worst = std::max(worst, std::abs(v[i] - (2.0 * (1.0 + i[0] + 100.0 * i[1]) + 1.0))); });
+    CHECK(worst == 0.0);
+    CHECK(u.evalAt(DS::MDIndex<2> {3, 4}) == 1.0 + 3 + 400.0);// u itself untouched by the sweep into v
+
+    // 2. Neumann ghost of a host-written field (updatePadding after the host loop): mirror value
+    CHECK(u.evalAt(DS::MDIndex<2> {-1, 5}) == u.evalAt(DS::MDIndex<2> {0, 5}));
+
+    // 3. rangeReduce with host lambdas over a device-computed field
+    auto sum = rangeReduce(v.assignableRange, [](auto&& a, auto&& b) { return a + b; }, [&](auto&& i) { return v[i]; });
+    double ref = 0;
+    for (int j = 0; j < n - 1; ++j)
+        for (int i = 0; i < n - 1; ++i) ref += 2.0 * (1.0 + i + 100.0 * j) + 1.0;
+    CHECK(std::abs(sum - ref) <= 1e-9 * std::abs(ref));
+#ifdef OPFLOW_B200_H// the reference only declares globalReduce in MPI builds (RangeFor.hpp:123-136)
+    auto gsum = globalReduce(v.assignableRange, [](auto&& a, auto&& b) { return a + b; }, [&](auto&& i) { return v[i]; });
+    CHECK(gsum == sum);
+#endif
+
+    // 4. copies are independent; compound and constant assignment
+    auto w = v;
+    w.name = "w";
+    w -= 1.0;
+    w /= 2.0;
+    worst = 0;
+    rangeFor_s(w.assignableRange, [&](auto&& i) { worst = std::max(worst, std::abs(w[i] - u[i])); });
+    CHECK(worst == 0.0);
+    CHECK(v.evalAt(DS::MDIndex<2> {1, 1}) == 2.0 * (1.0 + 1 + 100.0) + 1.0);
+    w = 0;
+    CHECK(w.evalAt(DS::MDIndex<2> {7, 9}) == 0.0);
+    w += u;
+    w = w - u;
+    auto wmax = rangeReduce(w.assignableRange, [](auto&& a, auto&& b) { return std::max(a, b); }, [&](auto&& i) { return std::abs(w[i]); });
+    CHECK(wmax == 0.0);
+
+    // 5. a device sweep after mixed host/device writes: conditional + comparison
+    w = conditional(u > 500.0, u, 0.0 * u);
+    int bad = 0;
+    rangeFor_s(w.assignableRange, [&](auto&& i) { bad += w[i] != (u[i] > 500.0 ? u[i] : 0.0); });
+    CHECK(bad == 0);
+
+    // 6. initBy uses cell-centre coordinates on Center axes (CartesianField.hpp:283-294)
+    w.initBy([](auto&& x) { return x[0] + 10.0 * x[1]; });
+    const double hx = 1.0 / (n - 1), hy = 2.0 / (n - 1);
+    CHECK(std::abs(w.evalAt(DS::MDIndex<2> {2, 3}) - ((2 + 0.5) * hx + 10.0 * (3 + 0.5) * hy)) < 1e-14);
+
+    std::printf(failures ? "FAILED %d\n" : "PASS\n", failures);
+    return failures ? 1 : 0;
+}

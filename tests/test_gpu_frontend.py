@@ -159,3 +159,11 @@ def test_reference_example_liddriven2d_unchanged(tmp_path):
             got, ref = got - got.mean(), ref - ref.mean()
         err = np.abs(got - ref).max() / np.abs(ref).max()
         assert err <= 1e-6, f"{name}: relative L-inf difference {err:.3e}"
+
+
+def test_host_access_semantics_program():
+    """tests/frontend/fe_hostaccess.cpp (host lambdas reading/writing device fields through operator[], copies, compound ops,
+    conditional, initBy): the same source prints PASS when built against the unmodified reference on the CPU (checked in the
+    authoring container with the oracle/build_ref.sh flags) -- here built against the B200 front-end"""
+    r = run("fe_hostaccess", mode="exact")
+    assert r.stdout.strip().endswith("PASS"), r.stdout[-2000:]
