@@ -83,6 +83,43 @@ def main():
             if abs(v[0] - ref) > 1e-11 * max(1.0, abs(ref)):
                 failures.append(f"{name} mode={mode}: global sum {v[0]!r} vs {ref!r}")
             del g, s, eg, es
+    # ---- EvenSplitStrategy blocks (the reference's default strategy: 2 x 2 blocks in 2-D on 4 ranks, with edge / corner
+    # neighbours -> the generic, non-overlapped exchange; an x-split on 2 ranks -> sub-boxes shifted along the fastest axis)
+    for name, dims in (("even split 2-D", (70, 52)), ("even split 3-D", (38, 30, 26))):
+        dim = len(dims)
+        for mode in (capi.MODE_EXACT, capi.MODE_FAST):
+            host.set_mode(mode)
+
+            def mk2(split):
+                mb = host.MeshBuilder(dim).newMesh(*dims)
+                for d in range(dim):
+                    mb.setMeshOfDim(d, 0., 1. + d)
+                mesh = mb.build()
+                b = host.ExprBuilder().setName("u").setMesh(mesh).setLoc([1] * dim).setExt(1).setPadding(1)
+                for d in range(dim):
+                    b.setBC(d, 0, host.BCType.Dirc, 1.).setBC(d, 1, host.BCType.Neum, 0.25)
+                if split:
+                    b.setSplitStrategy(world, rank, host.split_even(mesh, world))
+                return b.build()
+
+            g, sf = mk2(False), mk2(True)
+            full, lr = g.localRange, sf.localRange
+            init = np.random.default_rng(21).standard_normal(full.shape(dim))
+            g.from_numpy(init)
+            sl = tuple(slice(lr.start[d] - full.start[d], lr.end[d] - full.start[d]) for d in range(dim))
+            sf.from_numpy(init[sl])
+            c = 0.05 * min((1. + d) / (dims[d] - 1) for d in range(dim)) ** 2
+            lapg = d2x(D2, g) + d2y(D2, g) if dim == 2 else d2x(D2, g) + d2y(D2, g) + d2z(D2, g)
+            laps = d2x(D2, sf) + d2y(D2, sf) if dim == 2 else d2x(D2, sf) + d2y(D2, sf) + d2z(D2, sf)
+            for _ in range(8):
+                g.assign(g + c * lapg)
+                sf.assign(sf + c * laps)
+            a_, r_ = sf.to_numpy(), g.to_numpy()[sl]
+            if not np.array_equal(a_, r_):
+                failures.append(f"{name} mode={mode}: block differs, max abs {np.abs(a_ - r_).max():.3e} (neighbours: {len(sf.neighbors())})")
+            elif rank == 0 and mode == capi.MODE_EXACT:
+                print(f"  {name}: {len(sf.neighbors())} neighbours on rank 0, block {lr.tup(dim)}", flush=True)
+            del g, sf
     # ---- implicit path on a decomposed target: PCG + geometric multigrid with distributed levels (halo exchange per level, global
     # dot products / mean projections, replicated coarse hierarchy behind one allreduce) against the same solve on one GPU
     from opflow_b200.host import EqnSolveHandler, StructSolverType as ST
