@@ -62,19 +62,6 @@ namespace {
         if (r__ != 0) return opfe::fail(OPF_ERR_COMM, "%s: %s", #call, nc().GetErrorString(r__));                     \
     } while (0)
 
-    // pack / unpack one box between the pitched field storage and a dense staging buffer (K6)
-    __global__ void __launch_bounds__(256) box_copy_kernel(double* field, long long s1, long long s2, double* stage,
-                                                           opf::LaunchRange r, int to_stage) {
-        const long long n0 = r.hi[0] - r.lo[0], n1 = r.hi[1] - r.lo[1], n2 = r.hi[2] - r.lo[2];
-        const long long total = n0 * n1 * n2;
-        for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
-            const long long o = (r.lo[0] + t % n0) + (r.lo[1] + (t / n0) % n1) * s1 + (r.lo[2] + t / (n0 * n1)) * s2;
-            if (to_stage) stage[t] = field[o];
-            else
-                field[o] = stage[t];
-        }
-    }
-
     int inverse_code(int code, int dim) {
         int out = 0, p = 1;
         for (int d = 0; d < dim; ++d) {
@@ -104,7 +91,6 @@ namespace opfe {
         Nccl& n = nc();
         if (f->neighbors.empty()) return OPF_OK;
         if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
-        Context& c = ctx();
         const int nn = (int) f->neighbors.size();
         // staging layout: sends in neighbour order, recvs in neighbour order
         std::vector<long long> soff(nn + 1, 0), roff(nn + 1, 0);
@@ -120,22 +106,12 @@ namespace opfe {
             OPF_CUDA(cudaMalloc(&f->halo_recv, sizeof(double) * need));
             f->halo_elems = need;
         }
-        double* fb = f->biased(f->cur);
-        auto lr = [](const Range& r) {
-            opf::LaunchRange o;
-            for (int d = 0; d < 3; ++d) {
-                o.lo[d] = r.start[d];
-                o.hi[d] = r.end[d];
-            }
-            return o;
+        auto dense = [&](const Range& r, double* stage, bool unpack) {// rows / planes from the grid, axis 0 coalesced
+            const long long n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1];
+            return dense_convert(f, f->cur, stage, r, n0, n0 * n1, unpack, st);
         };
-        for (int i = 0; i < nn; ++i) {
-            const long long cnt = soff[i + 1] - soff[i];
-            const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
-            box_copy_kernel<<<blocks, 256, 0, st>>>(fb, f->pitch1, f->pitch2, f->halo_send + soff[i], lr(f->neighbors[i].send), 1);
-            c.launches++;
-        }
-        OPF_CUDA(cudaGetLastError());
+        for (int i = 0; i < nn; ++i)
+            if (int rc = dense(f->neighbors[i].send, f->halo_send + soff[i], false)) return rc;
         // message order per peer: sender's shift code ascending on both sides (the reference matches by tag =
         // hash(recv range), CartesianField.hpp:689-716)
         std::vector<int> sorder(nn), rorder(nn);
@@ -156,13 +132,9 @@ namespace opfe {
         }
         OPF_NCCL(n.GroupEnd());
         for (int i = 0; i < nn; ++i) {
-            const long long cnt = roff[i + 1] - roff[i];
-            if (cnt <= 0) continue;
-            const int blocks = (int) std::min<long long>((cnt + 255) / 256, 4LL * c.sm_count);
-            box_copy_kernel<<<blocks, 256, 0, st>>>(fb, f->pitch1, f->pitch2, f->halo_recv + roff[i], lr(f->neighbors[i].recv), 0);
-            c.launches++;
+            if (roff[i + 1] - roff[i] <= 0) continue;
+            if (int rc = dense(f->neighbors[i].recv, f->halo_recv + roff[i], true)) return rc;
         }
-        OPF_CUDA(cudaGetLastError());
         return OPF_OK;
     }
 }// namespace opfe
