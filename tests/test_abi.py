@@ -99,3 +99,110 @@ def test_signature_generation_matches_grammar():
     assert sig == "Add<F<0>,Mul<S<0>,Add<D2C<0,F<1>>,D2C<1,F<2>>>>>" and len(fields) == 3 and scalars == [0.1]
     e = u - 0.5 * host.dx(host.D1WENO53Downwind, u)
     assert e.signature() == "Sub<F<0>,Mul<S<0>,WenoDn<0,F<1>>>>"
+
+
+# ---- host logic through the real C ABI, on the CPU: opf_field_plan needs no device --------------------------------------------
+def _plan(dims, lo, hi, coords, loc, bc, ext, split=None):
+    dim = len(dims)
+    mb = host.MeshBuilder(dim).newMesh(*dims)
+    for d in range(dim):
+        mb.setMeshOfDim(d, coords[d]) if coords is not None else mb.setMeshOfDim(d, lo[d], hi[d])
+    b = host.ExprBuilder().setMesh(mb.build()).setLoc(loc).setExt(ext)
+    for (d, s), (t, v) in bc.items():
+        if t != capi.BC_UNDEFINED:
+            b.setBC(d, s, t, v)
+    if split:
+        b.setPadding(max(1, ext)).setSplitStrategy(*split)
+    return b.plan()
+
+
+def _rng(r, dim):
+    return [list(r.tup(dim)[0]), list(r.tup(dim)[1])]
+
+
+def test_range_classification_table_bit_exact_on_cpu():
+    """every row of the reference's range table (ExprBuilder::calculateRanges, CartesianField.hpp:950-1003) as dumped by the
+    unmodified reference (tests/golden/ref_fields.json: loc x BC start x BC end x ext x uniform/stretched mesh)"""
+    from test_oracle_pinned import BC, stretched
+    n_checked = 0
+    for c in REF["ranges1d"]:
+        n = c["n"]
+        bc = {(0, 0): (BC[c["bc"][0]], c["bcv"][0]), (0, 1): (BC[c["bc"][1]], c["bcv"][1])}
+        u = _plan([n], [0.0], [2.0], [stretched(n)] if c["stretched"] else None, c["loc"], bc, c["ext"])
+        r = c["ranges"]
+        assert _rng(u.localRange, 1) == r["local"] and _rng(u.assignableRange, 1) == r["assignable"], c
+        assert _rng(u.accessibleRange, 1) == r["accessible"] and _rng(u.logicalRange, 1) == r["logical"] and u.padding == r["padding"], c
+        n_checked += 1
+    assert n_checked == len(REF["ranges1d"]) and n_checked >= 100
+    for c in REF["ghost2d"]:
+        nx, ny = c["dims"]
+        bc = {}
+        for d in range(2):
+            t0, v0, t1, v1 = c["bc"][d]
+            bc[(d, 0)], bc[(d, 1)] = (BC[t0], float(v0)), (BC[t1], float(v1))
+        u = _plan([nx, ny], [0.0, 0.0], [2.0, 1.0], None, c["loc"], bc, c["ext"])
+        for key, got in (("local", u.localRange), ("assignable", u.assignableRange), ("accessible", u.accessibleRange), ("logical", u.logicalRange)):
+            assert _rng(got, 2) == c["ranges"][key], (c["loc"], c["bc"], key)
+
+
+def test_prepared_expression_ranges_bit_exact_on_cpu():
+    """Expr::prepare() range algebra and result location of every stencil operator and of the FTCS / WENO expressions
+    (opf_expr_prepare on plan-only fields) against the unmodified reference's dump"""
+    l = capi.lib()
+    bc = {(0, 0): (capi.BC_DIRC, 1.0), (0, 1): (capi.BC_NEUM, 0.0), (1, 0): (capi.BC_NEUM, 0.0), (1, 1): (capi.BC_DIRC, 0.0)}
+    for c in REF["prepare2d"]:
+        u = _plan([12, 10], [0.0, 0.0], [2.0, 1.0], None, c["loc"], bc, 3)
+        nf = c["sig"].count("F<")
+        F = (C.c_void_p * nf)(*[u.h] * nf)
+        for which, key in ((capi.R_ACCESSIBLE, "acc"), (capi.R_LOCAL, "local"), (capi.R_LOGICAL, "logical")):
+            r, loc = capi.Range(), (C.c_int * 3)()
+            capi.check(l.opf_expr_prepare(c["sig"].encode(), F, nf, which, C.byref(r), loc))
+            assert _rng(r, 2) == c[key] and list(loc)[:2] == c["eloc"], (c["sig"], key)
+
+
+def test_expression_errors_are_reported_not_swallowed():
+    """operands at different mesh locations abort in the reference (BinOpDefMacros.hpp.in:25-42): here OPF_ERR_LOC; malformed and
+    unknown signatures are OPF_ERR_INVALID; a plan-only field refuses device work"""
+    l = capi.lib()
+    bc = {(d, s): (capi.BC_DIRC, 0.0) for d in range(2) for s in range(2)}
+    a = _plan([9, 9], [0., 0.], [1., 1.], None, [0, 0], bc, 1)
+    b = _plan([9, 9], [0., 0.], [1., 1.], None, [1, 0], bc, 1)
+    F = (C.c_void_p * 2)(a.h, b.h)
+    r = capi.Range()
+    assert l.opf_expr_prepare(b"Add<F<0>,F<1>>", F, 2, capi.R_ACCESSIBLE, C.byref(r), None) == 6  # OPF_ERR_LOC
+    assert b"loc" in l.opf_last_error()
+    assert l.opf_expr_prepare(b"D1C<0,F<1>>", F, 2, capi.R_ACCESSIBLE, C.byref(r), None) == 0  # Center -> Corner on axis 0
+    assert l.opf_expr_prepare(b"Add<F<0>,D1C<0,F<1>>>", F, 2, capi.R_ACCESSIBLE, C.byref(r), None) == 0  # now both Corner
+    for bad in (b"Add<F<0>", b"Foo<F<0>>", b"D2C<7,F<0>>", b"Add<F<0>,F<1>>>"):
+        assert l.opf_expr_prepare(bad, F, 2, capi.R_ACCESSIBLE, C.byref(r), None) == 2, bad  # OPF_ERR_INVALID
+    rc = l.opf_field_update_padding(a.h)
+    assert rc != 0  # no device here (OPF_ERR_NO_DEVICE) or, on a GPU box, "field is a plan"
+
+
+def test_slab_and_even_split_neighbours_on_cpu():
+    """updateNeighbors (CartesianField.hpp:298-347) through plan-only fields: a 4-rank slab split has 1 neighbour at the ends and 2
+    inside; the reference's EvenSplitStrategy on 4 ranks in 2-D gives 2 x 2 blocks with 3 neighbours each (two edges, one corner);
+    send boxes lie inside the local block, receive boxes outside it"""
+    bc = {(d, s): (capi.BC_DIRC, 0.0) for d in range(3) for s in range(2)}
+    mesh = host.MeshBuilder(3).newMesh(17, 17, 33).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).setMeshOfDim(2, 0., 2.).build()
+    for rank, want in ((0, 1), (1, 2), (2, 2), (3, 1)):
+        b = host.ExprBuilder().setMesh(mesh).setPadding(1)
+        for (d, s), (t, v) in bc.items():
+            b.setBC(d, s, t, v)
+        u = b.setSplitStrategy(4, rank, host.split_slab(mesh, 4)).plan()
+        nb = u.neighbors()
+        assert len(nb) == want and all(abs(p - rank) == 1 for p, *_ in nb)
+        lo, hi = u.localRange.tup(3)
+        for p, send, recv, code in nb:
+            assert all(lo[d] <= send[0][d] and send[1][d] <= hi[d] for d in range(3))
+            assert recv[0][2] >= hi[2] or recv[1][2] <= lo[2]
+    mesh2 = host.MeshBuilder(2).newMesh(33, 33).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).build()
+    for rank in range(4):
+        b = host.ExprBuilder().setMesh(mesh2).setLoc([1, 1]).setExt(1).setPadding(1)
+        for d in range(2):
+            for s in range(2):
+                b.setBC(d, s, capi.BC_DIRC, 0.0)
+        u = b.setSplitStrategy(4, rank, host.split_even(mesh2, 4)).plan()
+        assert len(u.neighbors()) == 3
+        sizes = sorted((s[1][0] - s[0][0]) * (s[1][1] - s[0][1]) for _, s, _, _ in u.neighbors())
+        assert sizes == [1, 16, 16]  # one corner cell, two 16-cell edges
