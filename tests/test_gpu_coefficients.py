@@ -11,37 +11,7 @@ from opflow_b200.host import D2SecondOrderCentered as D2, d2x, d2y
 
 pytestmark = pytest.mark.gpu
 
-GOLD = {
-    "Dirc": dict(
-        ptr=[0, 3, 7, 11, 14, 18, 23, 28, 32, 36, 41, 46, 50, 53, 57, 61, 64],
-        col=[0, 1, 4, 0, 1, 2, 5, 1, 2, 3, 6, 2, 3, 7, 0, 4, 5, 8, 1, 4, 5, 6, 9, 2, 5, 6, 7, 10, 3, 6, 7, 11, 4, 8, 9, 12, 5, 8, 9, 10, 13, 6, 9, 10,
-             11, 14, 7, 10, 11, 15, 8, 12, 13, 9, 12, 13, 14, 10, 13, 14, 15, 11, 14, 15],
-        val=[6, -1, -1, -1, 5, -1, -1, -1, 5, -1, -1, -1, 6, -1, -1, 5, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, 5, -1,
-             -1, 5, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, 5, -1, -1, 6, -1, -1, -1, 5, -1, -1, -1, 5, -1, -1, -1, 6],
-        rhs=[-1] * 16, pinned_last=False),
-    "Neum": dict(
-        ptr=[0, 3, 7, 11, 14, 18, 23, 28, 32, 36, 41, 46, 50, 53, 57, 61, 62],
-        col=[0, 1, 4, 0, 1, 2, 5, 1, 2, 3, 6, 2, 3, 7, 0, 4, 5, 8, 1, 4, 5, 6, 9, 2, 5, 6, 7, 10, 3, 6, 7, 11, 4, 8, 9, 12, 5, 8, 9, 10, 13, 6,
-             9, 10, 11, 14, 7, 10, 11, 15, 8, 12, 13, 9, 12, 13, 14, 10, 13, 14, 15, 15],
-        val=[2, -1, -1, -1, 3, -1, -1, -1, 3, -1, -1, -1, 2, -1, -1, 3, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, 3, -1,
-             -1, 3, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, 3, -1, -1, 2, -1, -1, -1, 3, -1, -1, -1, 3, -1, 1],
-        rhs=[-1] * 15 + [0], pinned_last=True),
-    "Periodic": dict(
-        ptr=[0, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50, 55, 60, 65, 70, 75, 76],
-        col=[0, 1, 3, 4, 12, 0, 1, 2, 5, 13, 1, 2, 3, 6, 14, 0, 2, 3, 7, 15, 0, 4, 5, 7, 8, 1, 4, 5, 6, 9, 2, 5, 6, 7, 10, 3, 4, 6,
-             7, 11, 4, 8, 9, 11, 12, 5, 8, 9, 10, 13, 6, 9, 10, 11, 14, 7, 8, 10, 11, 15, 0, 8, 12, 13, 15, 1, 9, 12, 13, 14, 2, 10, 13, 14, 15, 15],
-        val=[4, -1, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, -1, 4, -1, -1, -1, 4, -1, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, -1,
-             4, -1, -1, 4, -1, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, -1, -1, -1, -1, 4, -1, -1, -1, 4, -1, -1, -1, -1, -1, 4, -1, -1, -1, -1, 4, -1, 1],
-        rhs=[-1] * 15 + [0], pinned_last=True),
-}
-
-
-def dense(g):
-    a = np.zeros((16, 16))
-    for r in range(16):
-        for k in range(g["ptr"][r], g["ptr"][r + 1]):
-            a[r, g["col"][k]] = g["val"][k]
-    return a
+from csr_golden import GOLD, dense
 
 
 @pytest.mark.parametrize("bc", ["Dirc", "Neum", "Periodic"])
