@@ -264,6 +264,7 @@ struct opf_solver_s {
         opf_field_s *r, *z;
         unsigned parity;// bit l: which buffer of level l's iterate is current (the fused sweep ping-pongs it)
         unsigned parity_after;// the same after the V-cycle: a replay must flip the host-side `cur` flags like the captured run did
+        int mode;             // arithmetic mode the captured kernels were instantiated for (opf_set_mode may change between solves)
         cudaGraphExec_t exec;
         long long launches;
         int calls;
@@ -511,9 +512,9 @@ namespace {
                 for (size_t lv = 1; lv < s->lv.size(); ++lv) parity |= (unsigned) s->lv[lv].x->cur << lv;
                 Solver::VGraph* g = nullptr;
                 for (auto& e : s->vgraphs)
-                    if (e.r == r && e.z == z && e.parity == parity) g = &e;
+                    if (e.r == r && e.z == z && e.parity == parity && e.mode == ctx().mode) g = &e;
                 if (!g) {
-                    s->vgraphs.push_back(Solver::VGraph{r, z, parity, parity, nullptr, 0, 0});
+                    s->vgraphs.push_back(Solver::VGraph{r, z, parity, parity, ctx().mode, nullptr, 0, 0});
                     g = &s->vgraphs.back();
                 }
                 Context& c = ctx();
