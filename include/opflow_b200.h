@@ -53,8 +53,12 @@ typedef enum { OPF_MESHEXT_UNDEFINED = 0, OPF_MESHEXT_SYMM = 1, OPF_MESHEXT_PERI
  *   EXACT  every +,-,*,/ is the IEEE-rn operation in the reference's order, no FMA contraction: explicit updates are
  *          bit-identical to the reference's CPU path.
  *   FAST   per-axis reciprocal coefficient arrays replace the divides of D2SecondOrderCentered / WENO53; FMA allowed;
- *          within 1e-12 relative of the reference (BASELINE.json north_star tolerance). */
-typedef enum { OPF_MODE_EXACT = 0, OPF_MODE_FAST = 1 } opf_mode;
+ *          within 1e-12 relative of the reference (BASELINE.json north_star tolerance).
+ *   STENCIL the reference's implicit-path arithmetic: EXACT, except that a / b is a * (1. / b) as in StencilPad::operator/
+ *          (StencilPad.hpp:293-296).  Probing the matrix-free operator in this mode yields the reference's assembled CSR / HYPRE
+ *          coefficients and right-hand side bit for bit on any mesh; EXACT reproduces them only where the reciprocals are exact
+ *          (dx a power of two).  Verification mode: direct-global skeleton only. */
+typedef enum { OPF_MODE_EXACT = 0, OPF_MODE_FAST = 1, OPF_MODE_STENCIL = 2 } opf_mode;
 typedef enum { OPF_RED_SUM = 0, OPF_RED_MAX = 1, OPF_RED_MIN = 2, OPF_RED_ABSMAX = 3, OPF_RED_SUMSQ = 4 } opf_reduce_op;
 
 typedef struct opf_range { int start[OPF_MAX_DIM], end[OPF_MAX_DIM]; } opf_range;
@@ -75,6 +79,15 @@ int opf_get_mode(void);
 int opf_synchronize(void);
 void* opf_stream(void);             /* the engine's compute cudaStream_t (for callers that launch their own kernels) */
 long long opf_launch_count(void);   /* kernels launched by this library since opf_init (bench.py gpu_launches) */
+/* Name of the kernel skeleton the most recent assignment launched ("opf::tma_kernel", "opf::tma2d_kernel", "opf::window_kernel",
+ * "opf::assign_kernel"): lets bench.py and the tests report what actually ran instead of assuming it. */
+const char* opf_last_kernel_name(void);
+/* Run-time switches for A/B runs and tests; each starts from the environment variable OPF_<KEY> or its default (1):
+ * "tma", "tma2d", "window" (skeleton selection), "overlap" (halo exchange overlapped with the interior sweep), "graphs" (CUDA-graph
+ * replay of the multigrid cycle), "mg_fused", "direct_halo" (contiguous slab faces sent straight from field storage),
+ * "fused_krylov" (device-resident PCG scalars).  opf_get_option returns -1 for an unknown key. */
+int opf_set_option(const char* key, int value);
+int opf_get_option(const char* key);
 /* CUDA-event timing on the engine's compute stream (bench.py): returns elapsed ms between begin and end */
 int opf_timer_begin(void);
 int opf_timer_end(float* ms);

@@ -20,7 +20,7 @@ POS_START, POS_END = 0, 1
 BC_UNDEFINED, BC_DIRC, BC_NEUM, BC_PERIODIC, BC_INTERNAL, BC_SYMM, BC_ASYMM = range(7)
 OP_EQ, OP_ADD, OP_MINUS, OP_MUL, OP_DIV = range(5)
 MESHEXT_UNDEFINED, MESHEXT_SYMM, MESHEXT_PERIODIC, MESHEXT_UNIFORM = range(4)
-MODE_EXACT, MODE_FAST = 0, 1
+MODE_EXACT, MODE_FAST, MODE_STENCIL = 0, 1, 2
 RED_SUM, RED_MAX, RED_MIN, RED_ABSMAX, RED_SUMSQ = range(5)
 R_LOCAL, R_ASSIGNABLE, R_ACCESSIBLE, R_LOGICAL, R_STORAGE, R_READABLE = range(6)
 (SOLVER_NONE, SOLVER_JACOBI, SOLVER_SMG, SOLVER_PFMG, SOLVER_CYCRED, SOLVER_PCG, SOLVER_GMRES, SOLVER_FGMRES,
@@ -89,6 +89,9 @@ SIGNATURES = {
     "opf_synchronize": (C.c_int, []),
     "opf_stream": (_V, []),
     "opf_launch_count": (C.c_longlong, []),
+    "opf_last_kernel_name": (C.c_char_p, []),
+    "opf_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "opf_get_option": (C.c_int, [C.c_char_p]),
     "opf_timer_begin": (C.c_int, []),
     "opf_timer_end": (C.c_int, [C.POINTER(C.c_float)]),
     "opf_mesh_create": (_V, [C.c_int, _I, _I, C.c_int]),

@@ -92,11 +92,36 @@ namespace opfe {
         if (f->neighbors.empty()) return OPF_OK;
         if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
         const int nn = (int) f->neighbors.size();
+        // Direct faces.  When the decomposition only cuts the slowest axis (slabs), every rank's storage has the same pitches and
+        // lead, and the `padding` planes (rows in 2-D) next to a neighbour are ONE contiguous run of the pitched buffer: they are
+        // sent straight from the field and received straight into the ghost planes -- no pack / unpack kernels, no staging
+        // ("each face is one contiguous block").  The run carries the planes' own ghost cells of the unsplit axes too;
+        // they land in the receiver's corner ghosts, which the reference leaves untouched and no stencil ever reads before the
+        // next fill.  Anything else (blocks, pencils, periodic images of a split axis with odd shapes) takes the staged route.
+        const int ax = f->dim - 1;
+        bool slab_layout = opf_internal_opt(OPF_OPT_DIRECT_HALO) != 0 && f->dim >= 2;
+        for (const auto& r : f->split_map)
+            for (int d = 0; d < ax && slab_layout; ++d)
+                if (r.start[d] != f->split_map[0].start[d] || r.end[d] != f->split_map[0].end[d]) slab_layout = false;
+        const long long plane = f->dim == 3 ? f->pitch2 : f->pitch1;// doubles per index of the slowest axis
+        auto spans_lower_axes = [&](const Range& r) {
+            for (int d = 0; d < ax; ++d)
+                if (r.start[d] != f->local.start[d] || r.end[d] != f->local.end[d]) return false;
+            return true;
+        };
+        std::vector<char> direct(nn, 0);
+        for (int i = 0; i < nn; ++i) {
+            const auto& nb = f->neighbors[i];
+            direct[i] = slab_layout && spans_lower_axes(nb.send) && nb.recv.count() > 0 && spans_lower_axes(nb.recv)
+                        && nb.send.end[ax] - nb.send.start[ax] == nb.recv.end[ax] - nb.recv.start[ax]
+                        && nb.recv.start[ax] >= f->storage.start[ax] && nb.recv.end[ax] <= f->storage.end[ax];
+        }
+        auto run_ptr = [&](int k) { return f->buf[f->cur] + f->lead + (long long) (k - f->storage.start[ax]) * plane; };
         // staging layout: sends in neighbour order, recvs in neighbour order
         std::vector<long long> soff(nn + 1, 0), roff(nn + 1, 0);
         for (int i = 0; i < nn; ++i) {
-            soff[i + 1] = soff[i] + f->neighbors[i].send.count();
-            roff[i + 1] = roff[i] + std::max<long long>(0, f->neighbors[i].recv.count());
+            soff[i + 1] = soff[i] + (direct[i] ? 0 : f->neighbors[i].send.count());
+            roff[i + 1] = roff[i] + (direct[i] ? 0 : std::max<long long>(0, f->neighbors[i].recv.count()));
         }
         const long long need = std::max(soff[nn], roff[nn]);
         if (need > f->halo_elems) {
@@ -111,7 +136,8 @@ namespace opfe {
             return dense_convert(f, f->cur, stage, r, n0, n0 * n1, unpack, st);
         };
         for (int i = 0; i < nn; ++i)
-            if (int rc = dense(f->neighbors[i].send, f->halo_send + soff[i], false)) return rc;
+            if (!direct[i])
+                if (int rc = dense(f->neighbors[i].send, f->halo_send + soff[i], false)) return rc;
         // message order per peer: sender's shift code ascending on both sides (the reference matches by tag =
         // hash(recv range), CartesianField.hpp:689-716)
         std::vector<int> sorder(nn), rorder(nn);
@@ -123,16 +149,21 @@ namespace opfe {
         OPF_NCCL(n.GroupStart());
         for (int k = 0; k < nn; ++k) {
             const int i = sorder[k];
-            OPF_NCCL(n.Send(f->halo_send + soff[i], (size_t) (soff[i + 1] - soff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, st));
+            const auto& nb = f->neighbors[i];
+            if (direct[i]) OPF_NCCL(n.Send(run_ptr(nb.send.start[ax]), (size_t) ((nb.send.end[ax] - nb.send.start[ax]) * plane), ncclFloat64, nb.rank, n.comm, st));
+            else
+                OPF_NCCL(n.Send(f->halo_send + soff[i], (size_t) (soff[i + 1] - soff[i]), ncclFloat64, nb.rank, n.comm, st));
         }
         for (int k = 0; k < nn; ++k) {
             const int i = rorder[k];
-            if (roff[i + 1] - roff[i] > 0)
-                OPF_NCCL(n.Recv(f->halo_recv + roff[i], (size_t) (roff[i + 1] - roff[i]), ncclFloat64, f->neighbors[i].rank, n.comm, st));
+            const auto& nb = f->neighbors[i];
+            if (direct[i]) OPF_NCCL(n.Recv(run_ptr(nb.recv.start[ax]), (size_t) ((nb.recv.end[ax] - nb.recv.start[ax]) * plane), ncclFloat64, nb.rank, n.comm, st));
+            else if (roff[i + 1] - roff[i] > 0)
+                OPF_NCCL(n.Recv(f->halo_recv + roff[i], (size_t) (roff[i + 1] - roff[i]), ncclFloat64, nb.rank, n.comm, st));
         }
         OPF_NCCL(n.GroupEnd());
         for (int i = 0; i < nn; ++i) {
-            if (roff[i + 1] - roff[i] <= 0) continue;
+            if (direct[i] || roff[i + 1] - roff[i] <= 0) continue;
             if (int rc = dense(f->neighbors[i].recv, f->halo_recv + roff[i], true)) return rc;
         }
         return OPF_OK;

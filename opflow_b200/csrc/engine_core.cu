@@ -82,6 +82,8 @@ int opf_init(int device) {
         if (!strcmp(m, "exact") || !strcmp(m, "EXACT") || !strcmp(m, "0")) c.mode = OPF_MODE_EXACT;
         else if (!strcmp(m, "fast") || !strcmp(m, "FAST") || !strcmp(m, "1"))
             c.mode = OPF_MODE_FAST;
+        else if (!strcmp(m, "stencil") || !strcmp(m, "STENCIL") || !strcmp(m, "2"))
+            c.mode = OPF_MODE_STENCIL;
     }
     c.inited = true;
     return OPF_OK;
@@ -105,7 +107,7 @@ int opf_finalize(void) {
 }
 
 int opf_set_mode(int mode) {
-    if (mode != OPF_MODE_EXACT && mode != OPF_MODE_FAST) return fail(OPF_ERR_INVALID, "bad mode %d", mode);
+    if (mode != OPF_MODE_EXACT && mode != OPF_MODE_FAST && mode != OPF_MODE_STENCIL) return fail(OPF_ERR_INVALID, "bad mode %d", mode);
     ctx().mode = mode;
     return OPF_OK;
 }
@@ -118,6 +120,50 @@ int opf_synchronize(void) {
 }
 void* opf_stream(void) { return ctx().stream; }
 long long opf_launch_count(void) { return ctx().launches; }
+
+// ---- run-time switches (A/B runs, tests): "tma", "tma2d", "window", "overlap", "graphs", "mg_fused", "direct_halo", "fused_krylov".
+// Each starts from the environment variable OPF_<KEY> (upper case) or its default.
+namespace {
+    struct Opt {
+        const char* key;
+        const char* env;
+        int dflt, value;
+        bool loaded;
+    };
+    Opt g_opts[OPF_OPT_COUNT] = {{"tma", "OPF_TMA", 1, 1, false},         {"tma2d", "OPF_TMA2D", 1, 1, false},
+                                 {"window", "OPF_WINDOW", 1, 1, false},   {"overlap", "OPF_OVERLAP", 1, 1, false},
+                                 {"graphs", "OPF_GRAPHS", 1, 1, false},   {"mg_fused", "OPF_MG_FUSED", 1, 1, false},
+                                 {"direct_halo", "OPF_DIRECT_HALO", 1, 1, false}, {"fused_krylov", "OPF_FUSED_KRYLOV", 1, 1, false}};
+    const char* g_last_kernel = "";
+}// namespace
+int opf_internal_opt(int id) {
+    if (id < 0 || id >= OPF_OPT_COUNT) return 0;
+    Opt& o = g_opts[id];
+    if (!o.loaded) {
+        const char* e = getenv(o.env);
+        o.value = e ? atoi(e) : o.dflt;
+        o.loaded = true;
+    }
+    return o.value;
+}
+void opf_internal_note_kernel(const char* name) { g_last_kernel = name; }
+const char* opf_last_kernel_name(void) { return g_last_kernel; }
+int opf_set_option(const char* key, int value) {
+    if (!key) return fail(OPF_ERR_INVALID, "null option key");
+    for (auto& o : g_opts)
+        if (!strcmp(o.key, key)) {
+            o.value = value;
+            o.loaded = true;
+            return OPF_OK;
+        }
+    return fail(OPF_ERR_INVALID, "unknown option '%s'", key);
+}
+int opf_get_option(const char* key) {
+    if (!key) return -1;
+    for (int i = 0; i < OPF_OPT_COUNT; ++i)
+        if (!strcmp(g_opts[i].key, key)) return opf_internal_opt(i);
+    return -1;
+}
 int opf_timer_begin(void) {
     if (int rc = require_device()) return rc;
     OPF_CUDA(cudaEventRecord(ctx().ev0, ctx().stream));
@@ -361,6 +407,7 @@ namespace {
         FillParams op[6];
         long long start[7];
         int n, lww;
+        int recip;// OPF_MODE_STENCIL: a / b evaluated as a * (1. / b) like StencilPad::operator/ (StencilPad.hpp:293-296)
     };
     __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ MultiFill mf) {
         const long long total_all = mf.start[mf.n];
@@ -419,7 +466,8 @@ namespace {
                         xg = __dadd_rn(p.x[gi], __ddiv_rn(p.dx[gi], 2.));
                     }
                     const double x1 = __dsub_rn(p.x[p.xb], xg), x2 = __dsub_rn(xm, xg);
-                    v = __ddiv_rn(__dsub_rn(__dmul_rn(x1, um), __dmul_rn(x2, bcv)), __dsub_rn(x1, x2));
+                    const double num = __dsub_rn(__dmul_rn(x1, um), __dmul_rn(x2, bcv)), den = __dsub_rn(x1, x2);
+                    v = mf.recip ? __dmul_rn(num, __ddiv_rn(1.0, den)) : __ddiv_rn(num, den);
                     break;
                 }
                 case 2: {// Neumann: u[m] + bc * (x_g - x_m)
@@ -490,6 +538,7 @@ namespace opfe {
         MultiFill mf;
         mf.n = 0;
         mf.lww = lww;
+        mf.recip = ctx().mode == OPF_MODE_STENCIL;
         mf.start[0] = 0;
         for (size_t i = b; i < e && mf.n < 6; ++i) {
             FillOp op = ops[i];

@@ -518,6 +518,24 @@ namespace opfe {
             if (op.r.count() > 0) return true;
         return false;
     }
+    // Can opf_assign_host pipeline this (dst, input) pair in chunks along the slowest axis?  Undecomposed fields without ghost
+    // cells to refresh, or -- *dist -- slab decompositions along that axis shared by both fields: the two boundary chunks are
+    // uploaded first, the INPUT's halo planes are exchanged once they are on the device, the chunk sweeps / downloads then stream
+    // as on one GPU, and the destination's own halo exchange closes the call.
+    static bool hostpipe_qualifies(const opf_field_s* dst, const opf_field_s* inf, bool* dist) {
+        *dist = false;
+        if (dst->dim < 2 || has_ghost_fills(dst) || has_ghost_fills(inf) || !(inf->local == dst->local)) return false;
+        const int ax = dst->dim - 1;
+        if (dst->local.end[ax] - dst->local.start[ax] < 16) return false;
+        if (dst->neighbors.empty() && inf->neighbors.empty()) return true;
+        SlabPlan sp;
+        const Range w = common(dst->assignable, dst->local);
+        if (!comm_active() || !slab_plan(dst, w, sp) || sp.axis != ax) return false;
+        if (inf != dst && (inf->n_ranks != dst->n_ranks || inf->padding != dst->padding || inf->neighbors.size() != dst->neighbors.size())) return false;
+        if (dst->local.end[ax] - dst->local.start[ax] < 24) return false;// three chunks of eight planes
+        *dist = true;
+        return true;
+    }
     struct HostPipe {
         opf_field_s* in_field;
         const double* host_in;
@@ -678,8 +696,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     li.alias0 = alias0;
     li.rop = -1;
     // register-window skeleton: vector loads need 16-byte aligned rows at the first evaluated cell
-    static const int window_on = getenv("OPF_WINDOW") ? atoi(getenv("OPF_WINDOW")) : 1;
-    li.window = window_on && dst->dim >= 2 && (w.end[0] - w.start[0]) >= 8;
+    li.window = opf_internal_opt(OPF_OPT_WINDOW) && dst->dim >= 2 && (w.end[0] - w.start[0]) >= 8;
     li.valign = 0;
     for (int k = 0; k < p->tree.nfields; ++k) {
         const opf_field_s* f = fields[k];
@@ -732,12 +749,14 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
         const int ax = dst->dim - 1;
         opf_field_s* inf = hp.in_field;
         const int nz = dst->local.end[ax] - dst->local.start[ax];
-        const bool simple = dst->dim >= 2 && dst->neighbors.empty() && !has_ghost_fills(dst) && !has_ghost_fills(inf) && inf->neighbors.empty() && inf->local == dst->local && nz >= 16 && !(flags & OPF_ASSIGN_NO_PADDING);
+        bool dist = false;
+        const bool simple = hostpipe_qualifies(dst, inf, &dist) && !(flags & OPF_ASSIGN_NO_PADDING);
         if (simple) {
             Context& c = ctx();
             PipeStreams* ps;
             if (int rc = pipe_streams(&ps)) return rc;
-            const int nch = std::min(16, nz / 8);
+            static const int max_chunks = getenv("OPF_PIPE_CHUNKS") ? std::max(2, std::min(32, atoi(getenv("OPF_PIPE_CHUNKS")))) : 32;
+            const int nch = std::max(dist ? 3 : 1, std::min(max_chunks, nz / 8));
             int radius = 0;// reach of the expression along the pipelined axis (planes of the next chunk a sweep needs)
             {
                 int lo[OPF_MAX_FIELDS][D3], hi[OPF_MAX_FIELDS][D3];
@@ -778,7 +797,9 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
             if (dbg && !te[0])
                 for (auto& ev : te) cudaEventCreate(&ev);
             if (dbg) cudaEventRecord(te[0], ps->h2d);
-            for (int ci = 0; ci < nch; ++ci) {
+            for (int k = 0; k < nch; ++k) {
+                // decomposed: the two boundary chunks first (their planes feed the input's halo exchange)
+                const int ci = !dist ? k : (k == 0 ? 0 : (k == 1 ? nch - 1 : k - 1));
                 OPF_CUDA(cudaMemcpyAsync(ps->stage_in + off(zcut(ci)), hp.host_in + off(zcut(ci)), sizeof(double) * (size_t) (off(zcut(ci + 1)) - off(zcut(ci))),
                                          cudaMemcpyHostToDevice, ps->h2d));
                 OPF_CUDA(cudaEventRecord(ps->up[ci], ps->h2d));
@@ -788,8 +809,13 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
             const int in_buf = inf->cur;// the buffer the sweep reads (dst's `cur` flips below when dst is in_field and ping-pongs)
             OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[0], 0));
             if (int rc = convert(inf, in_buf, ps->stage_in, zcut(0), zcut(1), true)) return rc;
+            if (dist) {// input halo: both boundary chunks are on the device -> exchange the planes the neighbours' sweeps tap
+                OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[nch - 1], 0));
+                if (int rc = convert(inf, in_buf, ps->stage_in, zcut(nch - 1), zcut(nch), true)) return rc;
+                if (int rc = halo_exchange(inf, c.stream)) return rc;
+            }
             for (int ci = 0; ci < nch; ++ci) {
-                if (ci + 1 < nch) {// the sweep of slab ci taps the first planes of slab ci+1
+                if (ci + 1 < nch && !(dist && ci + 1 == nch - 1)) {// the sweep of slab ci taps the first planes of slab ci+1
                     OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[ci + 1], 0));
                     if (int rc = convert(inf, in_buf, ps->stage_in, zcut(ci + 1), zcut(ci + 2), true)) return rc;
                 }
@@ -808,6 +834,10 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
                                          cudaMemcpyDeviceToHost, ps->d2h));
             }
             dst->bc0_clean[dst->cur] = true;
+            if (dist) {// updatePadding() of the result: halo planes of the new values (downloads of the last chunks still in flight)
+                if (int rc = halo_exchange(dst, c.stream)) return rc;
+                if (int rc = field_fill_periodic(dst)) return rc;
+            }
             if (dbg) cudaEventRecord(te[3], c.stream);
             if (dbg) cudaEventRecord(te[4], ps->d2h);
             OPF_CUDA(cudaStreamSynchronize(ps->d2h));
@@ -829,8 +859,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     //   compute stream: interior sweep, BC fill of its planes ............................................ | wait(comm)
     //   comm stream   : boundary-slab sweeps, BC fill of those planes, pack -> NCCL send/recv -> unpack
     SlabPlan sp;
-    static const int overlap_on = getenv("OPF_OVERLAP") ? atoi(getenv("OPF_OVERLAP")) : 1;
-    if (overlap_on && !(flags & OPF_ASSIGN_NO_PADDING) && comm_active() && slab_plan(dst, w, sp)) {
+    if (opf_internal_opt(OPF_OPT_OVERLAP) && !(flags & OPF_ASSIGN_NO_PADDING) && comm_active() && slab_plan(dst, w, sp)) {
         Context& c = ctx();
         // the boundary slabs, their BC fills and the whole exchange run on the high-priority stream, concurrently with the
         // interior sweep on the compute stream (disjoint planes of the destination; both read the old buffer)
@@ -865,19 +894,27 @@ int opf_assign_host(opf_field_t dst, int op, const char* signature, const opf_fi
     int rc = OPF_OK;
     const opf_range lr_in = to_c(in_field->local), lr_out = to_c(dst->local);
     // the pipelined route consumes the request inside opf_assign_ex; otherwise: plain upload -> assign -> download
-    const bool try_pipe = dst->dim >= 2 && dst->neighbors.empty() && !has_ghost_fills(dst) && !has_ghost_fills(in_field) && in_field->neighbors.empty() && in_field->local == dst->local
-                          && dst->local.end[dst->dim - 1] - dst->local.start[dst->dim - 1] >= 16;
+    bool dist_unused = false;
+    const bool try_pipe = hostpipe_qualifies(dst, in_field, &dist_unused);
+    auto sequential = [&]() -> int {
+        // upload -> updatePadding of the input (BC ghosts, halo planes: the uploaded values ARE the field now) -> assign -> download
+        if (int r2 = opf_field_upload(in_field, &lr_in, host_in)) return r2;
+        if (has_ghost_fills(in_field) || !in_field->neighbors.empty())
+            if (int r2 = field_update_padding(in_field)) return r2;
+        if (int r2 = opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0)) return r2;
+        return opf_field_download(dst, &lr_out, host_out);
+    };
     if (!try_pipe) {
         g_hostpipe = nullptr;
-        if ((rc = opf_field_upload(in_field, &lr_in, host_in))) return rc;
-        if ((rc = opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0))) return rc;
-        return opf_field_download(dst, &lr_out, host_out);
+        return sequential();
     }
     rc = opf_assign_ex(dst, op, signature, fields, nfields, scalars, nscalars, 0);
     g_hostpipe = nullptr;
     if (rc) return rc;
-    if (!hp.done) return fail(OPF_ERR_INVALID, "opf_assign_host: internal error, the pipelined route was not taken");
-    return OPF_OK;
+    if (hp.done) return OPF_OK;
+    // the launch description did not qualify for the pipelined route (e.g. a block decomposition): opf_assign_ex has then run the
+    // plain assignment on the field's OLD contents -- not what this call means.  That cannot happen silently:
+    return fail(OPF_ERR_INVALID, "opf_assign_host: internal error, the pipelined route was not taken");
 }
 
 int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src) {

@@ -506,7 +506,7 @@ namespace {
                     L0.b = sb, L0.x = sx;
                     return rc;
                 };
-                static const int graphs_on = getenv("OPF_GRAPHS") ? atoi(getenv("OPF_GRAPHS")) : 1;
+                const int graphs_on = opf_internal_opt(OPF_OPT_GRAPHS);
                 if (!graphs_on || s->lv[0].dist) return body();// NCCL exchanges inside: not captured
                 unsigned parity = (unsigned) z->cur;
                 for (size_t lv = 1; lv < s->lv.size(); ++lv) parity |= (unsigned) s->lv[lv].x->cur << lv;
@@ -780,7 +780,7 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
         }
         s->smooth_coef_leaf = coef_leaf;
         s->smooth_sig = "Add<F<0>,Mul<S<0>,Mul<F<1>,Sub<F<2>," + sm + ">>>>";
-        static const int fused_on = getenv("OPF_MG_FUSED") ? atoi(getenv("OPF_MG_FUSED")) : 1;
+        const int fused_on = opf_internal_opt(OPF_OPT_MG_FUSED);
         s->has_smooth_sig = fused_on && (int) coef_leaf.size() + 3 <= OPF_MAX_FIELDS && n_lhs_scalars + 1 <= OPF_MAX_SCALARS
                             && opf_expr_is_registered(s->smooth_sig.c_str()) != 0;
     }
@@ -957,26 +957,30 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     opf_field_s* t = s->target;
     const Range w = common(t->assignable, t->local);
     // ---- setup (once when static_mat, else every solve -- the reference re-creates the HYPRE solver every time)
+    // constant part of an affine lhs (multigrid levels only exist for pure operators, which have none).  Measured on EVERY solve,
+    // static_mat or not: a coefficient field's contents may change between solves without its handle changing, and the reference
+    // rebuilds the bias every time as well (generateb, HYPREEqnSolveHandler.hpp:199) -- one operator application.
+    {
+        s->pin_active = false;
+        s->affine = false;
+        bool pure = true;
+        for (size_t k = 0; k < s->lhs_fields.size(); ++k)
+            if (!((s->mask >> k) & 1u)) pure = false;
+        if (!pure || !s->lhs_scalars.empty()) {
+            if (!s->C0 && !(s->C0 = clone_homogeneous(t, "kry.c0"))) return OPF_ERR_CUDA;
+            if (int rc = assign(s->Z, "S<0>", {}, {0.0})) return rc;
+            if (int rc = apply_lhs(s, s->Z, s->C0, 0, false)) return rc;
+            double cmax = 0;
+            opf_field_t F[1] = {s->C0};
+            opf_range cr = to_c(w);
+            if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &cmax)) return rc;
+            if (s->lv[0].dist)
+                if (int rc = opf_comm_allreduce(&cmax, 1, OPF_RED_MAX)) return rc;
+            s->affine = cmax != 0.0;
+        }
+    }
     if (!s->setup_done || !s->params.static_mat) {
         s->pin_active = false;
-        {// constant part of an affine lhs (multigrid levels only exist for pure operators, which have none)
-            s->affine = false;
-            bool pure = true;
-            for (size_t k = 0; k < s->lhs_fields.size(); ++k)
-                if (!((s->mask >> k) & 1u)) pure = false;
-            if (!pure || !s->lhs_scalars.empty()) {
-                if (!s->C0 && !(s->C0 = clone_homogeneous(t, "kry.c0"))) return OPF_ERR_CUDA;
-                if (int rc = assign(s->Z, "S<0>", {}, {0.0})) return rc;
-                if (int rc = apply_lhs(s, s->Z, s->C0, 0, false)) return rc;
-                double cmax = 0;
-                opf_field_t F[1] = {s->C0};
-                opf_range cr = to_c(w);
-                if (int rc = opf_reduce(OPF_RED_ABSMAX, "F<0>", F, 1, nullptr, 0, &cr, &cmax)) return rc;
-                if (s->lv[0].dist)
-                    if (int rc = opf_comm_allreduce(&cmax, 1, OPF_RED_MAX)) return rc;
-                s->affine = cmax != 0.0;
-            }
-        }
         // a multigrid request on an operator that cannot be coarsened (coefficient fields, decomposed target) degrades to its
         // level-0 smoother, i.e. Jacobi: the diagonal is needed then as well
         const bool wants_mg = s->params.precond == OPF_SOLVER_PFMG || s->params.precond == OPF_SOLVER_SMG || s->params.type == OPF_SOLVER_PFMG

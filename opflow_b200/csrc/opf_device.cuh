@@ -22,6 +22,13 @@
 #include <math.h>
 #include <cstdlib>
 
+// run-time switches and launch bookkeeping live in libopflow_b200.so (engine_core.cu); launchers instantiated in a user's
+// translation unit reach them through these two C symbols
+enum { OPF_OPT_TMA = 0, OPF_OPT_TMA2D, OPF_OPT_WINDOW, OPF_OPT_OVERLAP, OPF_OPT_GRAPHS, OPF_OPT_MG_FUSED, OPF_OPT_DIRECT_HALO,
+       OPF_OPT_FUSED_KRYLOV, OPF_OPT_COUNT };
+extern "C" int opf_internal_opt(int id);
+extern "C" void opf_internal_note_kernel(const char* name);
+
 namespace opf {
 
     constexpr int MAX_FIELDS = 32;
@@ -93,6 +100,13 @@ namespace opf {
         __device__ __forceinline__ static double sub(double a, double b) { return __dsub_rn(a, b); }
         __device__ __forceinline__ static double mul(double a, double b) { return __dmul_rn(a, b); }
         __device__ __forceinline__ static double div(double a, double b) { return __ddiv_rn(a, b); }
+    };
+    // Stencil -- the arithmetic of the reference's IMPLICIT path: StencilPad's `pad / num` is `pad * (1. / num)`
+    // (src/DataStructures/StencilPad.hpp:293-296), so a coefficient the assembled matrix holds is a*(1/d), one rounding away from the
+    // explicit path's a/d whenever d is not a power of two.  Probing the operator in this mode reproduces the reference's assembled
+    // CSR / HYPRE coefficients bit for bit on any mesh (tests/test_gpu_coefficients.py against tests/golden/ref_csr.json).
+    struct Stencil : Exact {
+        __device__ __forceinline__ static double div(double a, double b) { return __dmul_rn(a, __ddiv_rn(1.0, b)); }
     };
     struct Fast {
         static constexpr bool fast = true;
@@ -1267,6 +1281,7 @@ namespace opf {
         static const int pd = getenv("OPF_WPD") ? atoi(getenv("OPF_WPD")) : 8;
         auto go = [&](auto kern) {
             kern<<<grid, block, 0, st>>>(a, li.dst, li.old, li.r, ch, li.op, li.valign, li.dalign, pd);
+            opf_internal_note_kernel("opf::window_kernel");
             return (int) cudaGetLastError();
         };
         if (li.uniform) {// single-spacing axes: coefficients from the constant bank
@@ -1311,6 +1326,7 @@ namespace opf {
         auto go = [&](auto kern) {
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
             kern<<<grid, block, smem, st>>>(a, maps, li.dst, li.old, li.r, ch, li.op, li.dalign);
+            opf_internal_note_kernel("opf::tma_kernel");
             return (int) cudaGetLastError();
         };
         if (li.uniform) {
@@ -1330,6 +1346,7 @@ namespace opf {
         if constexpr (E::maxaxis < 1 && (DIMS & 1))
             if (li.dim == 1) {
                 assign_kernel<E, P, A0, 1><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                opf_internal_note_kernel("opf::assign_kernel");
                 return (int) cudaGetLastError();
             }
         if constexpr (E::maxaxis < 2 && (DIMS & 2))
@@ -1337,14 +1354,14 @@ namespace opf {
                 if constexpr (WinInfo<E, A0, 2>::ok && E::nf > 0)
                     if (li.window) return launch_window<E, P, A0, 2>(a, li, st);
                 assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                opf_internal_note_kernel("opf::assign_kernel");
                 return (int) cudaGetLastError();
             }
         if constexpr ((DIMS & 4) != 0)
         if (li.dim == 3) {
             if constexpr (WinInfo<E, A0, 3>::ok && E::nf > 0) {
                 // TMA tile skeleton: footprint must fit the ring/box budget (<= 200 KB of shared memory)
-                static const int tma_on = getenv("OPF_TMA") ? atoi(getenv("OPF_TMA")) : 1;
-                if (tma_on && li.window && li.tma_ok && (li.r.hi[0] - li.r.lo[0]) >= 64) {
+                if (opf_internal_opt(OPF_OPT_TMA) && li.window && li.tma_ok && (li.r.hi[0] - li.r.lo[0]) >= 64) {
 #ifdef OPF_TMA_SWEEP
                     // tuning build: tile shape selectable at run time (OPF_TBY in {4,8}, OPF_TCX in {2,4})
                     static const int tby = getenv("OPF_TBY") ? atoi(getenv("OPF_TBY")) : OPF_TMA_BY;
@@ -1364,9 +1381,33 @@ namespace opf {
                 if (li.window) return launch_window<E, P, A0, 3>(a, li, st);
             }
             assign_kernel<E, P, A0, 3><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+            opf_internal_note_kernel("opf::assign_kernel");
             return (int) cudaGetLastError();
         }
         return -2;// expression uses an axis the field does not have
+    }
+    // direct-global skeleton only (Stencil arithmetic: a verification mode, not a fast path)
+    template <class E, class P, bool A0, int DIMS>
+    int launch_assign_plain(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
+        const LaunchGeom g = assign_geometry(li);
+        if (g.grid.x == 0) return 0;
+        opf_internal_note_kernel("opf::assign_kernel");
+        if constexpr (E::maxaxis < 1 && (DIMS & 1))
+            if (li.dim == 1) {
+                assign_kernel<E, P, A0, 1><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                return (int) cudaGetLastError();
+            }
+        if constexpr (E::maxaxis < 2 && (DIMS & 2))
+            if (li.dim == 2) {
+                assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                return (int) cudaGetLastError();
+            }
+        if constexpr ((DIMS & 4) != 0)
+            if (li.dim == 3) {
+                assign_kernel<E, P, A0, 3><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                return (int) cudaGetLastError();
+            }
+        return -2;
     }
     template <class E, class P, bool A0>
     int launch_reduce(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
@@ -1385,8 +1426,13 @@ namespace opf {
         constexpr bool can_alias = E::nf > 1;
         if (li.rop >= 0) {
             if constexpr (can_alias)
-                if (li.alias0) return li.mode == 0 ? launch_reduce<E, Exact, true>(a, li, st) : launch_reduce<E, Fast, true>(a, li, st);
-            return li.mode == 0 ? launch_reduce<E, Exact, false>(a, li, st) : launch_reduce<E, Fast, false>(a, li, st);
+                if (li.alias0) return li.mode != 1 ? launch_reduce<E, Exact, true>(a, li, st) : launch_reduce<E, Fast, true>(a, li, st);
+            return li.mode != 1 ? launch_reduce<E, Exact, false>(a, li, st) : launch_reduce<E, Fast, false>(a, li, st);
+        }
+        if (li.mode == 2) {// OPF_MODE_STENCIL
+            if constexpr (can_alias)
+                if (li.alias0) return launch_assign_plain<E, Stencil, true, DIMS>(a, li, st);
+            return launch_assign_plain<E, Stencil, false, DIMS>(a, li, st);
         }
         if constexpr (can_alias)
             if (li.alias0) return li.mode == 0 ? launch_assign<E, Exact, true, DIMS>(a, li, st) : launch_assign<E, Fast, true, DIMS>(a, li, st);

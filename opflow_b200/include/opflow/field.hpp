@@ -659,13 +659,15 @@ namespace OpFlow {
             return *this;
         }
         // setBC(d, pos, type) for logical BCs, setBC(d, pos, type, value) for Dirc / Neum (CartesianField.hpp:827-895)
-        auto& setBC(int d, DimPos pos, BCType type) {
+        auto& setBC(int d, DimPos pos, BCType type) {// only the requested side, like the reference (CartesianField.hpp:827-850)
             (pos == DimPos::start ? f.bc[d].start : f.bc[d].end) = BCInfo {type, 0.};
-            if (type == BCType::Periodic) f.bc[d].start = f.bc[d].end = BCInfo {type, 0.};
             return *this;
         }
         template <Meta::Numerical T>
         auto& setBC(int d, DimPos pos, BCType type, T val) {
+            // logical types forward to the value-less overload (the reference's own tests use this form,
+            // CSRMatrixGeneratorMPITest.cpp:389)
+            if (type == BCType::Periodic || type == BCType::Symm || type == BCType::ASymm) return setBC(d, pos, type);
             if (type != BCType::Dirc && type != BCType::Neum) {
                 OP_ERROR("BC type not supported.");
                 OP_ABORT;

@@ -5,7 +5,13 @@
 // OMPI_/PMI_ equivalents).  MPI_Init becomes: pick the GPU, create the NCCL communicator (id exchanged through a file).
 #pragma once
 #include "field.hpp"
+#include <cctype>
+#include <cstring>
+#include <ctime>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <thread>
+#include <unistd.h>
 
 namespace OpFlow {
     using ParallelType = unsigned;
@@ -55,6 +61,24 @@ namespace OpFlow {
         inline int env_rank() { return env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"}, 0); }
         inline int env_world() { return env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"}, 1); }
         inline int env_local_rank() { return env_int({"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"}, env_rank()); }
+        // what every rank of ONE job shares and two jobs do not: an explicit id, the elastic run id, the batch job id, or -- for the
+        // ranks torchrun / mpirun fork on one node -- the launcher's process id
+        inline std::string job_nonce() {
+            for (const char* n : {"OPF_JOB_ID", "TORCHELASTIC_RUN_ID", "SLURM_JOB_ID", "PMIX_NAMESPACE"})
+                if (const char* v = std::getenv(n))
+                    if (*v && std::string(v) != "none") {
+                        std::string out;
+                        for (const char* c = v; *c && out.size() < 40; ++c) out.push_back(std::isalnum((unsigned char) *c) ? *c : '-');
+                        return out;
+                    }
+            return "ppid" + std::to_string((long) ::getppid());
+        }
+        struct RendezvousRecord {
+            char magic[8];
+            char nonce[48];
+            long long stamp;
+            unsigned char id[128];
+        };
     }// namespace internal
 
     inline int getWorkerId() { return opf_comm_rank(); }
@@ -65,26 +89,57 @@ namespace OpFlow {
         const int world = internal::env_world(), rank = internal::env_rank();
         internal::check_rc(opf_init(world > 1 ? internal::env_local_rank() : -1), "opf_init");
         if (world <= 1) return;
-        // rendezvous: rank 0 publishes the ncclUniqueId in a file every rank of the job can see
+        // rendezvous: rank 0 publishes the ncclUniqueId in a file every rank of the job can see.  The record carries a per-job
+        // nonce and rank 0's publication time, the file is created exclusively (O_EXCL | O_NOFOLLOW, mode 0600) under a name that
+        // includes the user id and the nonce, and readers only accept a regular file owned by themselves whose nonce matches and
+        // whose time stamp is not older than their own start: a stale file left by a crashed job is neither read nor followed.
+        // Multi-node jobs (no shared /tmp) must point OPF_RENDEZVOUS_DIR at a shared directory and set OPF_JOB_ID.
         const char* dir = std::getenv("OPF_RENDEZVOUS_DIR");
-        const std::string path = std::string(dir ? dir : "/tmp") + "/opflow_b200_nccl_" + std::to_string(internal::env_int({"MASTER_PORT", "SLURM_JOB_ID"}, 0))
-                                 + "_" + std::to_string(world) + ".id";
+        const std::string nonce = internal::job_nonce();
+        const std::string path = std::string(dir ? dir : "/tmp") + "/opflow_b200_nccl_u" + std::to_string((long) ::geteuid()) + "_" + nonce + "_"
+                                 + std::to_string(internal::env_int({"MASTER_PORT"}, 0)) + "_" + std::to_string(world) + ".id";
+        internal::RendezvousRecord rec{};
         unsigned char id[128];
+        const long long t_start = (long long) ::time(nullptr);
         if (rank == 0) {
             internal::check_rc(opf_comm_unique_id(id), "opf_comm_unique_id");
+            std::memcpy(rec.magic, "OPFNCCL1", 8);
+            std::snprintf(rec.nonce, sizeof rec.nonce, "%s", nonce.c_str());
+            rec.stamp = (long long) ::time(nullptr);
+            std::memcpy(rec.id, id, sizeof id);
             const std::string tmp = path + ".tmp";
-            std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char*>(id), sizeof id);
-            std::rename(tmp.c_str(), path.c_str());
+            ::unlink(path.c_str());// a stale record of a crashed job with the same name
+            ::unlink(tmp.c_str());
+            const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+            if (fd < 0 || ::write(fd, &rec, sizeof rec) != (ssize_t) sizeof rec) {
+                OP_CRITICAL("InitEnvironment: cannot publish the NCCL id at {}", tmp);
+                OP_ABORT;
+            }
+            ::close(fd);
+            if (std::rename(tmp.c_str(), path.c_str()) != 0) {
+                OP_CRITICAL("InitEnvironment: cannot rename {} -> {}", tmp, path);
+                OP_ABORT;
+            }
         } else {
             for (int tries = 0;; ++tries) {
-                std::ifstream in(path, std::ios::binary);
-                if (in && in.read(reinterpret_cast<char*>(id), sizeof id)) break;
-                if (tries > 6000) {
-                    OP_CRITICAL("InitEnvironment: no NCCL id at {} after 60 s", path);
+                bool ok = false;
+                const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+                if (fd >= 0) {
+                    struct stat st {};
+                    if (::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_uid == ::geteuid() && st.st_size == (off_t) sizeof rec
+                        && ::read(fd, &rec, sizeof rec) == (ssize_t) sizeof rec && std::memcmp(rec.magic, "OPFNCCL1", 8) == 0
+                        && nonce == std::string(rec.nonce, ::strnlen(rec.nonce, sizeof rec.nonce)) && rec.stamp >= t_start - 600)
+                        ok = true;
+                    ::close(fd);
+                }
+                if (ok) break;
+                if (tries > 12000) {
+                    OP_CRITICAL("InitEnvironment: no valid NCCL id at {} after 120 s (multi-node: set OPF_RENDEZVOUS_DIR to a shared directory and OPF_JOB_ID)", path);
                     OP_ABORT;
                 }
                 std::this_thread::sleep_for(std::chrono::milliseconds(10));
             }
+            std::memcpy(id, rec.id, sizeof id);
         }
         internal::check_rc(opf_comm_init(rank, world, id), "opf_comm_init");
         double one = 1.0;// doubles as a barrier: every rank has joined before rank 0 removes the file

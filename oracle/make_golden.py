@@ -41,7 +41,7 @@ def main():
     out = subprocess.run([os.path.join(BIN, "ref_fields")], env=ENV, capture_output=True, text=True, check=True)
     json.loads(out.stdout)  # validate
     open(os.path.join(GOLD, "ref_fields.json"), "w").write(out.stdout)
-    for drv in ("ref_implicit",):
+    for drv in ("ref_implicit", "ref_csr"):
         exe = os.path.join(BIN, drv)
         if os.path.exists(exe):
             out = subprocess.run([exe], env=ENV, capture_output=True, text=True, check=True)

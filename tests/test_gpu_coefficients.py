@@ -53,3 +53,87 @@ def test_probed_operator_equals_reference_csr(engine, bc, mode):
     q.assign(lap)
     rhs = -(1.0 - q.to_numpy(ar).reshape(-1, order="F"))
     assert np.array_equal(rhs[rows], np.asarray(GOLD[bc]["rhs"], dtype=float)[rows])
+
+
+def _stretched(n, scale):
+    s = np.arange(n) / (n - 1)
+    return scale * (s + 0.15 * np.sin(2 * np.pi * s) / (2 * np.pi))
+
+
+def _ref_csr_cases():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_csr.json")
+    return json.load(open(path))["cases"]
+
+
+@pytest.mark.parametrize("case", _ref_csr_cases(), ids=lambda c: f"{'stretched' if c['stretched'] else 'uniform'}-{'center' if c['loc'] else 'corner'}-bc{c['bc']}")
+def test_probed_operator_on_non_unit_spacing(engine, case):
+    """Same probe on meshes whose spacing is NOT 1 (7 x 6 nodes on [0,0.7] x [0,1.3], uniform and stretched) against CSR matrices
+    assembled by the unmodified reference (oracle/ref_drivers/ref_csr.cpp -> tests/golden/ref_csr.json, hex doubles).
+    The reference's implicit path divides a StencilPad by multiplying with the reciprocal (StencilPad.hpp:293-296), its explicit path
+    divides: the two differ by one rounding inside the reference itself.  So the statement tested is:
+      STENCIL mode  coefficients and right-hand side bit-identical to the reference's assembled matrix;
+      EXACT mode    bit-identical to the reference's EXPLICIT operator (test_gpu_explicit.py), hence within 4 ulp of the matrix;
+      FAST mode     within 1e-12 relative (reciprocal coefficient arrays, FMA)."""
+    c = case
+    nx, ny = c["dims"]
+    mb = host.MeshBuilder(2).newMesh(nx, ny)
+    if c["stretched"]:
+        mb.setMeshOfDim(0, _stretched(nx, 0.7)).setMeshOfDim(1, _stretched(ny, 1.3))
+    else:
+        mb.setMeshOfDim(0, 0., 0.7).setMeshOfDim(1, 0., 1.3)
+    mesh = mb.build()
+
+    def mk(name, homogeneous):
+        b = host.ExprBuilder().setMesh(mesh).setName(name).setLoc([c["loc"]] * 2).setExt(1)
+        for d in range(2):
+            if c["bc"] == 0:
+                b.setBC(d, 0, host.BCType.Dirc, 0. if homogeneous else 0.25 * (d + 1)).setBC(d, 1, host.BCType.Dirc, 0. if homogeneous else -0.5)
+            elif c["bc"] == 1:
+                b.setBC(d, 0, host.BCType.Neum, 0. if homogeneous else 0.125).setBC(d, 1, host.BCType.Neum, 0.)
+            else:
+                b.setBC(d, 0, host.BCType.Periodic).setBC(d, 1, host.BCType.Periodic)
+        return b.build()
+
+    (s0, s1), (e0, e1) = c["range"]
+    n0, n1 = e0 - s0, e1 - s1
+    N = n0 * n1
+    G = np.zeros((N, N))
+    val = [float.fromhex(v) for v in c["val"]]
+    for r in range(N):
+        for k in range(c["ptr"][r], c["ptr"][r + 1]):
+            G[r, c["col"][k]] = val[k]
+    grhs = np.array([float.fromhex(v) for v in c["rhs"]])
+    rows = slice(0, N - 1) if c["pinned_last"] else slice(0, N)
+    ar = capi.Range.make([s0, s1], [e0, e1])
+    for mode in (capi.MODE_STENCIL, capi.MODE_EXACT, capi.MODE_FAST):
+        host.set_mode(mode)
+        e, q, er = mk("e", True), mk("q", True), mk("er", False)
+        assert e.assignableRange.tup(2) == ((s0, s1), (e0, e1))
+        lap = d2x(D2, e) + d2y(D2, e)
+        cols = []
+        for j in range(N):
+            unit = np.zeros((n0, n1), order="F")
+            unit[j % n0, j // n0] = 1.0
+            e.assign(0.0)
+            e.from_numpy(unit, ar)
+            q.assign(lap)
+            cols.append(q.to_numpy(ar).reshape(-1, order="F"))
+        A = -np.stack(cols, axis=1)
+        er.assign(0.0)  # e = 0 with the REAL boundary data: b = rhs - lhs(0) (generateb, HYPREEqnSolveHandler.hpp:125-179)
+        q.assign(d2x(D2, er) + d2y(D2, er))
+        rhs = -(1.0 - q.to_numpy(ar).reshape(-1, order="F"))
+        scale = np.abs(G).max()
+        if mode == capi.MODE_STENCIL:
+            assert np.array_equal(A[rows], G[rows]), f"STENCIL mode: {np.count_nonzero(A[rows] != G[rows])} coefficients differ from the reference CSR"
+            assert np.array_equal(rhs[rows], grhs[rows]), "STENCIL mode: right-hand side differs from the reference"
+            for r in range(N)[rows]:  # sparsity pattern, explicit zeros of the reference included only if it stores them
+                assert set(np.nonzero(A[r])[0].tolist()) <= set(c["col"][c["ptr"][r]:c["ptr"][r + 1]])
+        elif mode == capi.MODE_EXACT:
+            assert np.abs(A[rows] - G[rows]).max() <= 4 * np.finfo(float).eps * scale
+            assert np.abs(rhs[rows] - grhs[rows]).max() <= 16 * np.finfo(float).eps * max(1.0, np.abs(grhs).max())
+        else:
+            assert np.abs(A[rows] - G[rows]).max() <= 1e-12 * scale
+            assert np.abs(rhs[rows] - grhs[rows]).max() <= 1e-12 * max(1.0, np.abs(grhs).max())
+    host.set_mode(capi.MODE_FAST)
