@@ -194,8 +194,10 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
                   const double* scalars, int nscalars, int flags);
 /* The same assignment for callers whose data lives in HOST memory (pinned for full speed): the values of `in_field` over its
  * localRange come from host_in (axis 0 fastest, dense), dst (op)= expr is evaluated, and dst's localRange is written to host_out.
- * in_field is dst itself or one of the expression's leaves.  Upload, sweep and download are pipelined in slabs along the slowest
- * axis on three streams; returns when host_out is complete.  (The reference has no such call: its fields ARE host memory --
+ * in_field is dst itself or one of the expression's leaves; its ghost cells (BC extension, periodic images, halo planes of a
+ * decomposed field) are refreshed from the uploaded values before the sweep, as updatePadding() would.  Upload, sweep and download
+ * are pipelined in slabs along the slowest axis on three streams -- also for slab-decomposed fields, whose two boundary chunks travel
+ * first so that the input's halo exchange starts early; returns when host_out is complete.  (The reference has no such call: its fields ARE host memory --
  * this is what a caller that keeps PlainTensor storage on the host, CartesianField.hpp:37, would use per assignment.) */
 int opf_assign_host(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
                     int nscalars, opf_field_t in_field, const double* host_in, double* host_out);

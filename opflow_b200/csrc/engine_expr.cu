@@ -861,24 +861,55 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     SlabPlan sp;
     if (opf_internal_opt(OPF_OPT_OVERLAP) && !(flags & OPF_ASSIGN_NO_PADDING) && comm_active() && slab_plan(dst, w, sp)) {
         Context& c = ctx();
+        // OPF_HALO_DEBUG=1: event time line of the overlapped step (no profiler needed), printed every 50th call
+        static const bool hdbg = getenv("OPF_HALO_DEBUG") != nullptr;
+        static cudaEvent_t he[8] = {};
+        static long long hcalls = 0;
+        static double hacc[8] = {};
+        if (hdbg && !he[0])
+            for (auto& e : he) cudaEventCreate(&e);
+        auto mark = [&](int i, cudaStream_t st) {
+            if (hdbg) cudaEventRecord(he[i], st);
+        };
         // the boundary slabs, their BC fills and the whole exchange run on the high-priority stream, concurrently with the
         // interior sweep on the compute stream (disjoint planes of the destination; both read the old buffer)
         OPF_CUDA(cudaEventRecord(c.ev_compute, c.stream));
+        mark(0, c.stream);
         OPF_CUDA(cudaStreamWaitEvent(c.comm_stream, c.ev_compute, 0));
+        mark(1, c.comm_stream);
         if (int rc = launch_box(sp.lo, c.comm_stream)) return rc;
         if (int rc = launch_box(sp.hi, c.comm_stream)) return rc;
+        mark(2, c.comm_stream);
         if (int rc = launch_box(sp.mid)) return rc;
+        mark(5, c.stream);
         if (use_twin) dst->cur = wr;
         if (sp.has_lo)
             if (int rc = field_fill_bc(dst, &sp.clip_lo, c.comm_stream)) return rc;
         if (sp.has_hi)
             if (int rc = field_fill_bc(dst, &sp.clip_hi, c.comm_stream)) return rc;
+        mark(3, c.comm_stream);
         if (int rc = halo_exchange(dst, c.comm_stream)) return rc;
+        mark(4, c.comm_stream);
         OPF_CUDA(cudaEventRecord(c.ev_comm, c.comm_stream));
         if (int rc = field_fill_bc(dst, &sp.clip_mid)) return rc;
         dst->bc0_clean[dst->cur] = true;
         OPF_CUDA(cudaStreamWaitEvent(c.stream, c.ev_comm, 0));
-        return field_fill_periodic(dst);// unsplit periodic axes: local copies over the whole logical box, exchanged planes included
+        mark(6, c.stream);
+        const int prc = field_fill_periodic(dst);// unsplit periodic axes: local copies over the whole logical box, exchanged planes included
+        if (hdbg) {
+            cudaEventSynchronize(he[6]);
+            for (int i = 1; i <= 6; ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, he[0], he[i]);
+                hacc[i] += ms;
+            }
+            if (++hcalls % 50 == 0) {
+                fprintf(stderr, "[opf halo r%d] us from step start: comm-start %.1f | boundary sweeps done %.1f | fills %.1f | exchange done %.1f || interior sweep done %.1f | joined %.1f\n",
+                        dst->rank, 1e3 * hacc[1] / 50, 1e3 * hacc[2] / 50, 1e3 * hacc[3] / 50, 1e3 * hacc[4] / 50, 1e3 * hacc[5] / 50, 1e3 * hacc[6] / 50);
+                for (auto& a2 : hacc) a2 = 0;
+            }
+        }
+        return prc;
     }
     if (int rc = launch_box(w)) return rc;
     if (use_twin) dst->cur = wr;// ping-pong instead of the reference's temp copy + second sweep

@@ -40,10 +40,11 @@ def test_host_assign_equals_resident_assign(engine, dims, ext, mode):
     c = 0.02 * min((1. + 0.5 * d) / (dims[d] - 1) for d in range(dim)) ** 2
     steps = 3
     inits = [np.asfortranarray(rng.standard_normal(lr.shape(dim))) for _ in range(steps)]
-    # resident reference: upload (raw, no updatePadding -- what opf_assign_host does), assign, download
+    # resident reference: upload, updatePadding (the uploaded values ARE the field: its BC ghosts follow them), assign, download
     want = []
     for a in inits:
         r.upload_raw(a.ctypes.data, lr)
+        r.updatePadding()
         r.assign(r + c * lap(r, dim))
         want.append(r.to_numpy())
     sig, fields, scalars = (u + c * lap(u, dim)).flatten()
