@@ -957,7 +957,7 @@ int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src) {
 
 // launches the reduction; the result is left in device memory (*dev_result), valid until the next reduction on the stream
 static int reduce_launch(int rop, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
-                         const opf_range* range, double** dev_result, bool* empty) {
+                         const opf_range* range, double** dev_result, bool* empty, double* result_slot = nullptr) {
     if (!signature) return fail(OPF_ERR_INVALID, "null argument");
     if (rop < 0 || rop > 4) return fail(OPF_ERR_INVALID, "bad reduce op");
     if (int rc = require_device()) return rc;
@@ -988,10 +988,11 @@ static int reduce_launch(int rop, const char* signature, const opf_field_t* fiel
     const long long items = rows * ((r.end[0] - r.start[0] + opf::RED_SEG - 1) / opf::RED_SEG);
     li.n_partials = (int) std::max<long long>(1, std::min<long long>(items, 4LL * c.sm_count));
     li.partials = c.red_buf;
+    li.result = result_slot;
     const int rc = p->fn(&a, &li, c.stream);
     if (rc != 0) return fail(OPF_ERR_CUDA, "reduce launch of '%s' failed", p->sig.c_str());
     c.launches += 2;
-    *dev_result = c.red_buf + li.n_partials;
+    *dev_result = result_slot ? result_slot : c.red_buf + li.n_partials;
     return OPF_OK;
 }
 
@@ -1016,6 +1017,15 @@ int opf_reduce(int rop, const char* signature, const opf_field_t* fields, int nf
 
 namespace opfe {
     // device-resident sum of a field over a box (no host synchronisation): used by the multigrid mean projection
+    // device-resident dot product over a box: the folded value is written to `slot` (device memory), stream-ordered, no host
+    // synchronisation; an empty box writes nothing (callers pre-zero the slot)
+    int dot_device(opf_field_s* a, opf_field_s* b, const Range& r, double* slot) {
+        opf_field_t F[2] = {a, b};
+        opf_range cr = to_c(r);
+        bool empty = false;
+        double* dev = nullptr;
+        return reduce_launch(OPF_RED_SUM, "Mul<F<0>,F<1>>", F, 2, nullptr, 0, &cr, &dev, &empty, slot);
+    }
     int reduce_sum_device(opf_field_s* f, const Range& r, double** dev_result) {
         opf_field_t F[1] = {f};
         opf_range cr = to_c(r);

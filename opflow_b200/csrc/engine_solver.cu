@@ -23,6 +23,7 @@
 namespace opfe {
     int signature_radius(const char* sig);// engine_expr.cu
     int reduce_sum_device(opf_field_s* f, const Range& r, double** dev_result);
+    int dot_device(opf_field_s* a, opf_field_s* b, const Range& r, double* slot);
 }
 using namespace opfe;
 
@@ -216,6 +217,71 @@ namespace {
     __global__ void set_cell_kernel(double* u, long long off, double v) { u[off] = v; }
     __global__ void copy_cell_kernel(double* dst, const double* src, long long off) { dst[off] = src[off]; }
 
+    // ------------------------------------------------------------------------------------------------ device-resident PCG
+    // The Krylov scalars never visit the host: dot products fold into ks[], the update kernels form alpha / beta from them, and a
+    // control kernel decides whether the iteration continues -- through the condition of a CUDA-graph WHILE node when the whole
+    // iteration is captured (one graph launch per solve), through a mapped flag read once per iteration otherwise.
+    enum { KS_RZ = 0, KS_PQ, KS_RR, KS_RZN, KS_BNORM, KS_TOL, KS_COUNT = 8 };
+    struct PcgCtl {
+        int iters, maxit, cont, breakdown;
+        double rel;
+    };
+    // x += alpha p ; r -= alpha q ; partial sums of r.r          (48 B per cell instead of 24 + 24 + 8 in three passes)
+    __global__ void __launch_bounds__(256) pcg_update_kernel(double* __restrict__ x, const double* __restrict__ p, double* __restrict__ r,
+                                                             const double* __restrict__ q, long long s1, long long s2, opf::LaunchRange w,
+                                                             const double* __restrict__ ks, double* __restrict__ partials) {
+        const double pq = ks[KS_PQ];
+        const double alpha = pq != 0.0 ? ks[KS_RZ] / pq : 0.0;
+        const int n0 = w.hi[0] - w.lo[0], n1 = w.hi[1] - w.lo[1], n2 = w.hi[2] - w.lo[2];
+        const long long rows = (long long) n1 * n2;
+        double acc = 0.0;
+        for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+            const int j = w.lo[1] + (int) (row % n1), k = w.lo[2] + (int) (row / n1);
+            const long long o = (long long) w.lo[0] + (long long) j * s1 + (long long) k * s2;
+            for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+                x[o + i] += alpha * p[o + i];
+                const double rn = r[o + i] - alpha * q[o + i];
+                r[o + i] = rn;
+                acc += rn * rn;
+            }
+        }
+        acc = opf::block_reduce(0, acc);
+        if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    }
+    // folds the partials into ks[KS_RR], counts the iteration, decides continuation
+    __global__ void __launch_bounds__(256) pcg_control_kernel(const double* __restrict__ partials, int n, double* __restrict__ ks, PcgCtl* ctl,
+                                                              cudaGraphConditionalHandle handle, int use_cond, int allreduce_pending) {
+        double acc = 0.0;
+        if (partials) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+            acc = opf::block_reduce(0, acc);
+        }
+        if (threadIdx.x == 0) {
+            if (partials) ks[KS_RR] = acc;
+            if (!allreduce_pending) {
+                const double rr = ks[KS_RR];
+                const bool brk = ks[KS_PQ] == 0.0;// p.q == 0: the update kernel took alpha = 0, nothing moved
+                if (!brk) ctl->iters += 1;
+                const double rel = sqrt(rr) / ks[KS_BNORM];
+                ctl->rel = rel;
+                ctl->breakdown = brk;
+                const int cont = (rel > ks[KS_TOL]) && (ctl->iters < ctl->maxit) && !brk;
+                ctl->cont = cont;
+                if (use_cond) cudaGraphSetConditional(handle, cont ? 1u : 0u);
+            }
+        }
+    }
+    // p = z + beta p with beta = (r.z)_new / (r.z)_old
+    __global__ void __launch_bounds__(256) pcg_direction_kernel(double* __restrict__ p, const double* __restrict__ z, long long s1, long long s2,
+                                                                opf::LaunchRange w, const double* __restrict__ ks) {
+        const double beta = ks[KS_RZN] / ks[KS_RZ];
+        const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x0 >= w.hi[0] - w.lo[0]) return;
+        const long long o = (long long) (w.lo[0] + x0) + (long long) (w.lo[1] + (int) blockIdx.y) * s1 + (long long) (w.lo[2] + (int) blockIdx.z) * s2;
+        p[o] = z[o] + beta * p[o];
+    }
+    __global__ void pcg_shift_kernel(double* ks) { ks[KS_RZ] = ks[KS_RZN]; }
+
     // box launch: threads along axis 0, rows and planes from blockIdx.y / .z
     struct BoxGrid {
         dim3 grid, block;
@@ -270,6 +336,18 @@ struct opf_solver_s {
         int calls;
     };
     std::vector<VGraph> vgraphs;
+    // device-resident PCG state: scalars, control block (mapped pinned host memory), the captured WHILE-loop graphs
+    double* ks = nullptr;
+    PcgCtl* ctl_host = nullptr;
+    PcgCtl* ctl_dev = nullptr;
+    struct LoopGraph {
+        unsigned parity, parity_after;
+        int mode, precond, pin_active;
+        cudaGraphExec_t exec;
+        long long launches;
+    };
+    std::vector<LoopGraph> loops;
+    bool in_loop_capture = false;
     bool pinned = false;
     long long pin_off = 0;
     bool setup_done = false, mg = false, has_res_sig = false;
@@ -507,7 +585,7 @@ namespace {
                     return rc;
                 };
                 const int graphs_on = opf_internal_opt(OPF_OPT_GRAPHS);
-                if (!graphs_on || s->lv[0].dist) return body();// NCCL exchanges inside: not captured
+                if (!graphs_on || s->lv[0].dist || s->in_loop_capture) return body();// NCCL exchanges inside: not captured; inside the loop capture: inlined
                 unsigned parity = (unsigned) z->cur;
                 for (size_t lv = 1; lv < s->lv.size(); ++lv) parity |= (unsigned) s->lv[lv].x->cur << lv;
                 Solver::VGraph* g = nullptr;
@@ -844,15 +922,164 @@ static void drop_graphs(opf_solver_s* s) {
     for (auto& g : s->vgraphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     s->vgraphs.clear();
+    for (auto& g : s->loops)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->loops.clear();
 }
 
 int opf_solver_destroy(opf_solver_t s) {
     if (!s) return OPF_OK;
     drop_graphs(s);
+    if (s->ks) cudaFree(s->ks);
+    if (s->ctl_dev) cudaFree(s->ctl_dev);
+    if (s->ctl_host) cudaFreeHost(s->ctl_host);
     for (auto& L : s->lv) free_level_fields(L);
     for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0, s->C0})
         if (f) opf_field_destroy(f);
     delete s;
+    return OPF_OK;
+}
+
+
+// ---- device-resident PCG (see the kernels above).  One iteration, launched into the engine stream (plainly, or into a capture):
+//   q = A p ; pq = p.q ; x += (rz/pq) p ; r -= (rz/pq) q ; rr = r.r ; [control] ; z = M^-1 r ; rzn = r.z ; p = z + (rzn/rz) p ; rz = rzn
+static int pcg_body(opf_solver_s* s, const Range& w, cudaGraphConditionalHandle handle, int use_cond) {
+    Context& c = ctx();
+    const bool dist = s->lv[0].dist && comm_active();
+    if (int rc = apply_lhs(s, s->P, s->Q, 0)) return rc;
+    if (int rc = dot_device(s->P, s->Q, w, s->ks + KS_PQ)) return rc;
+    if (dist)
+        if (int rc = comm_allreduce_device(s->ks + KS_PQ, 1, OPF_RED_SUM, c.stream)) return rc;
+    const long long rows = (long long) (w.end[1] - w.start[1]) * (w.end[2] - w.start[2]);
+    const int nb = (int) std::max<long long>(1, std::min<long long>(rows, 4LL * c.sm_count));
+    opf_field_s *X = s->X, *P = s->P, *R = s->R, *Q = s->Q;
+    pcg_update_kernel<<<nb, 256, 0, c.stream>>>(X->biased(X->cur), P->biased(P->cur), R->biased(R->cur), Q->biased(Q->cur), X->pitch1, X->pitch2, lr_of(w), s->ks,
+                                                c.red_buf);
+    if (!dist) {
+        pcg_control_kernel<<<1, 256, 0, c.stream>>>(c.red_buf, nb, s->ks, s->ctl_dev, handle, use_cond, 0);
+        c.launches += 2;
+    } else {
+        pcg_control_kernel<<<1, 256, 0, c.stream>>>(c.red_buf, nb, s->ks, s->ctl_dev, handle, 0, 1);
+        if (int rc = comm_allreduce_device(s->ks + KS_RR, 1, OPF_RED_SUM, c.stream)) return rc;
+        pcg_control_kernel<<<1, 256, 0, c.stream>>>(nullptr, 0, s->ks, s->ctl_dev, handle, 0, 0);
+        c.launches += 3;
+    }
+    if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
+    if (int rc = dot_device(s->R, s->Z, w, s->ks + KS_RZN)) return rc;
+    if (dist)
+        if (int rc = comm_allreduce_device(s->ks + KS_RZN, 1, OPF_RED_SUM, c.stream)) return rc;
+    opf_field_s* Z = s->Z;
+    const BoxGrid bg = box_grid(w);
+    pcg_direction_kernel<<<bg.grid, bg.block, 0, c.stream>>>(P->biased(P->cur), Z->biased(Z->cur), P->pitch1, P->pitch2, lr_of(w), s->ks);
+    pcg_shift_kernel<<<1, 1, 0, c.stream>>>(s->ks);
+    c.launches += 2;
+    OPF_CUDA(cudaGetLastError());
+    return OPF_OK;
+}
+
+static unsigned loop_parity(opf_solver_s* s) {
+    unsigned pp = (unsigned) s->Z->cur;
+    for (size_t lv = 1; lv < s->lv.size(); ++lv) pp |= (unsigned) s->lv[lv].x->cur << lv;
+    return pp;
+}
+static void loop_apply_parity(opf_solver_s* s, unsigned pp) {
+    s->Z->cur = (int) (pp & 1u);
+    for (size_t lv = 1; lv < s->lv.size(); ++lv) s->lv[lv].x->cur = (int) ((pp >> lv) & 1u);
+}
+
+// PCG on the current operator with device-resident scalars.  rel0 / rr0: relative residual and r.r of the starting iterate (already
+// computed by the caller, s->R holds that residual).
+static int run_pcg_device(opf_solver_s* s, const Range& w, double bnorm, double tol, int maxit, double rr0, int* iters_io, double* rel_io) {
+    Context& c = ctx();
+    const bool dist = s->lv[0].dist && comm_active();
+    if (!s->ks) {
+        OPF_CUDA(cudaMalloc(&s->ks, sizeof(double) * KS_COUNT));
+        OPF_CUDA(cudaMalloc(&s->ctl_dev, sizeof(PcgCtl)));
+        OPF_CUDA(cudaMallocHost(&s->ctl_host, sizeof(PcgCtl)));
+    }
+    double init[KS_COUNT] = {0};
+    init[KS_RR] = rr0, init[KS_BNORM] = bnorm, init[KS_TOL] = tol, init[KS_PQ] = 1.0;
+    OPF_CUDA(cudaMemcpyAsync(s->ks, init, sizeof init, cudaMemcpyHostToDevice, c.stream));
+    *s->ctl_host = PcgCtl{*iters_io, maxit, 1, 0, *rel_io};
+    OPF_CUDA(cudaMemcpyAsync(s->ctl_dev, s->ctl_host, sizeof(PcgCtl), cudaMemcpyHostToDevice, c.stream));
+    // z = M^-1 r ; p = z ; rz = r.z
+    if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
+    if (int rc = assign(s->P, "F<0>", {s->Z}, {})) return rc;
+    if (int rc = dot_device(s->R, s->Z, w, s->ks + KS_RZ)) return rc;
+    if (dist)
+        if (int rc = comm_allreduce_device(s->ks + KS_RZ, 1, OPF_RED_SUM, c.stream)) return rc;
+    auto fetch = [&]() -> int {
+        OPF_CUDA(cudaMemcpyAsync(s->ctl_host, s->ctl_dev, sizeof(PcgCtl), cudaMemcpyDeviceToHost, c.stream));
+        OPF_CUDA(cudaStreamSynchronize(c.stream));
+        return OPF_OK;
+    };
+    const bool want_graph = opf_internal_opt(OPF_OPT_GRAPHS) && opf_internal_opt(OPF_OPT_FUSED_KRYLOV) >= 2 && !dist;
+    // the first iteration always runs as plain launches: every lazy allocation (twin buffers, reduction scratch, kernel attributes)
+    // happens here, outside any capture
+    if (int rc = pcg_body(s, w, 0, 0)) return rc;
+    if (int rc = fetch()) return rc;
+    while (s->ctl_host->cont) {
+        if (want_graph) {
+            const unsigned parity = loop_parity(s);
+            opf_solver_s::LoopGraph* g = nullptr;
+            for (auto& e : s->loops)
+                if (e.parity == parity && e.mode == c.mode && e.precond == s->params.precond && e.pin_active == (int) s->pin_active) g = &e;
+            if (!g) {
+                // capture the iteration as the body of a WHILE node: the control kernel sets the loop condition on the device
+                cudaGraph_t graph = nullptr;
+                OPF_CUDA(cudaGraphCreate(&graph, 0));
+                cudaGraphConditionalHandle handle;
+                OPF_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+                cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+                np.conditional.handle = handle;
+                np.conditional.type = cudaGraphCondTypeWhile;
+                np.conditional.size = 1;
+                cudaGraphNode_t node;
+                cudaError_t ce = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+                if (ce == cudaSuccess) ce = cudaStreamBeginCaptureToGraph(c.stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+                if (ce != cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    s->loops.push_back({parity, parity, c.mode, s->params.precond, (int) s->pin_active, nullptr, 0});// marks "do not try again"
+                    g = &s->loops.back();
+                } else {
+                    const long long l0 = c.launches;
+                    s->in_loop_capture = true;
+                    const int rc = pcg_body(s, w, handle, 1);
+                    s->in_loop_capture = false;
+                    cudaGraph_t done = nullptr;
+                    ce = cudaStreamEndCapture(c.stream, &done);
+                    const unsigned after = loop_parity(s);
+                    loop_apply_parity(s, parity);
+                    const long long nl = c.launches - l0;
+                    c.launches = l0;
+                    cudaGraphExec_t exec = nullptr;
+                    if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (rc) return rc;
+                    if (ce != cudaSuccess) {
+                        cudaGetLastError();
+                        exec = nullptr;
+                    }
+                    s->loops.push_back({parity, after, c.mode, s->params.precond, (int) s->pin_active, exec, nl});
+                    g = &s->loops.back();
+                }
+            }
+            if (g->exec) {
+                const int before = s->ctl_host->iters;
+                OPF_CUDA(cudaGraphLaunch(g->exec, c.stream));
+                if (int rc = fetch()) return rc;
+                const int ran = s->ctl_host->iters - before + (s->ctl_host->breakdown ? 1 : 0);
+                if (ran > 0) loop_apply_parity(s, g->parity_after);
+                c.launches += g->launches * std::max(ran, 1);
+                break;// the loop ran to its end on the device
+            }
+        }
+        if (int rc = pcg_body(s, w, 0, 0)) return rc;
+        if (int rc = fetch()) return rc;
+    }
+    *iters_io = s->ctl_host->iters;
+    *rel_io = s->ctl_host->rel;
     return OPF_OK;
 }
 
@@ -864,8 +1091,10 @@ static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm
     if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
     if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
     double rel = std::sqrt(rnorm2) / bnorm;
-    if (type == OPF_SOLVER_PCG) {
-        // preconditioned conjugate gradients, convergence on ||r||2 / ||b||2
+    if (type == OPF_SOLVER_PCG && opf_internal_opt(OPF_OPT_FUSED_KRYLOV) && rel > tol && iters < maxit) {
+        if (int rc = run_pcg_device(s, w, bnorm, tol, maxit, rnorm2, &iters, &rel)) return rc;
+    } else if (type == OPF_SOLVER_PCG) {
+        // preconditioned conjugate gradients, convergence on ||r||2 / ||b||2 (host-driven reference implementation of the loop)
         double rz = 0, rz_new = 0, pq = 0;
         if (rel > tol) {
             if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;

@@ -91,6 +91,7 @@ namespace opf {
         int rop;
         double* partials;// >= grid blocks
         int n_partials;
+        double* result;// where the folded value goes (device memory); null: partials + n_partials
     };
 
     // ------------------------------------------------------------------------------------------- policies
@@ -1413,7 +1414,7 @@ namespace opf {
     int launch_reduce(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
         const int nb = li.n_partials;
         reduce_kernel<E, P, A0><<<nb, 256, 0, st>>>(a, li.r, li.partials, li.rop);
-        reduce_final_kernel<0><<<1, 256, 0, st>>>(li.partials, nb, li.partials + nb, li.rop);
+        reduce_final_kernel<0><<<1, 256, 0, st>>>(li.partials, nb, li.result ? li.result : li.partials + nb, li.rop);
         return (int) cudaGetLastError();
     }
 
