@@ -792,6 +792,20 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
                 // dense strides follow the field's axes: axis 1 stride e0; axis 2 stride e0*e1 (unused in 2-D where axis 1 is pipelined)
                 return dense_convert(f, which, dense + off(z0), r, e0, e0 * e1, unpack, c.stream);
             };
+            // updatePadding() of the uploaded input, chunk by chunk: its Corner-Dirichlet boundary nodes take the BC value (step 0 of
+            // CartesianField.hpp:351-364; ghost-cell extensions do not exist on fields that qualify for this route)
+            auto fill_input = [&](int buf, int z0, int z1) -> int {
+                if (inf->fill0.empty()) return OPF_OK;
+                Range clip = inf->storage;
+                if (z0 > inf->local.start[ax]) clip.start[ax] = z0;
+                if (z1 < inf->local.end[ax]) clip.end[ax] = z1;
+                const int saved = inf->cur;
+                inf->cur = buf;// the fill addresses the buffer being uploaded even after dst (== inf) has flipped to its twin
+                inf->bc0_clean[buf] = false;
+                const int rc = field_fill_bc(inf, &clip, c.stream);
+                inf->cur = saved;
+                return rc;
+            };
             static const bool dbg = getenv("OPF_PIPE_DEBUG") != nullptr;
             static cudaEvent_t te[6] = {};
             if (dbg && !te[0])
@@ -809,15 +823,18 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
             const int in_buf = inf->cur;// the buffer the sweep reads (dst's `cur` flips below when dst is in_field and ping-pongs)
             OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[0], 0));
             if (int rc = convert(inf, in_buf, ps->stage_in, zcut(0), zcut(1), true)) return rc;
+            if (int rc = fill_input(in_buf, zcut(0), zcut(1))) return rc;
             if (dist) {// input halo: both boundary chunks are on the device -> exchange the planes the neighbours' sweeps tap
                 OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[nch - 1], 0));
                 if (int rc = convert(inf, in_buf, ps->stage_in, zcut(nch - 1), zcut(nch), true)) return rc;
+                if (int rc = fill_input(in_buf, zcut(nch - 1), zcut(nch))) return rc;
                 if (int rc = halo_exchange(inf, c.stream)) return rc;
             }
             for (int ci = 0; ci < nch; ++ci) {
                 if (ci + 1 < nch && !(dist && ci + 1 == nch - 1)) {// the sweep of slab ci taps the first planes of slab ci+1
                     OPF_CUDA(cudaStreamWaitEvent(c.stream, ps->up[ci + 1], 0));
                     if (int rc = convert(inf, in_buf, ps->stage_in, zcut(ci + 1), zcut(ci + 2), true)) return rc;
+                    if (int rc = fill_input(in_buf, zcut(ci + 1), zcut(ci + 2))) return rc;
                 }
                 Range box = w, clip = dst->storage;
                 box.start[ax] = std::max(w.start[ax], zcut(ci));

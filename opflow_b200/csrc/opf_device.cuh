@@ -459,9 +459,15 @@ namespace opf {
             const double s3 = 13. / 12. * t5 * t5 + t6 * t6 * 0.25;
             const double eps = 1e-6 * fmax(fmax(fmax(d1 * d1, d2 * d2), fmax(d3 * d3, d4 * d4)), d5 * d5) + 1e-99;
             const double e1 = s1 + eps, e2 = s2 + eps, e3 = s3 + eps;
-            // a_k = g_k / e_k^2 (e_k can be ~1e-99 on flat data: keep the reference's form, no cross-products that
-            // would underflow); one reciprocal of the sum instead of three divides
-            const double a1 = .1 / (e1 * e1), a2 = .6 / (e2 * e2), a3 = .3 / (e3 * e3);
+            // w_k = (g_k / e_k^2) / sum_j (g_j / e_j^2), with every a_k scaled by the common factor (e_2 e_3 / e_1)^2 * e_1^2 so that only TWO
+            // FP64 reciprocals remain (each costs ~12 FP64-pipe instructions; the kernel is FP64-pipe bound, ncu: 71 % pipe active):
+            //   f_k = e_k / e_1 ;  a_1 = .1 f_2^2 f_3^2 ;  a_2 = .6 f_3^2 ;  a_3 = .3 f_2^2
+            // e_k can be ~1e-99 on flat data, so raw cross products e_j^2 e_k^2 would underflow; the RATIOS cannot misbehave:
+            // eps <= e_k <= 33 max(d^2) + eps and eps >= 1e-6 max(d^2) bound e_k / e_1 by 3.3e7, f^2 f^2 by 1.2e30.
+            const double r1 = 1. / e1;
+            const double f2 = e2 * r1, f3 = e3 * r1;
+            const double g2 = f2 * f2, g3 = f3 * f3;
+            const double a1 = .1 * g2 * g3, a2 = .6 * g3, a3 = .3 * g2;
             const double inv = 1. / (a1 + a2 + a3);
             return (a1 * ddx1 + a2 * ddx2 + a3 * ddx3) * inv;
         } else {
