@@ -55,7 +55,7 @@ namespace {
 
     // per-axis prolongation weight of coarse cell I for fine cell i (cell-centred axes), shared by both transfer kernels so
     // that R = (1/2) P^T per axis exactly (a symmetric V-cycle is what lets it precondition CG)
-    __device__ __forceinline__ double cc_weight(const XferParams& p, int d, int i, int I) {
+    __host__ __device__ __forceinline__ double cc_weight(const XferParams& p, int d, int i, int I) {
         const int r = i - p.f0[d];
         const int par = p.c0[d] + (r >> 1);
         int nb = (r & 1) ? par + 1 : par - 1;
@@ -173,6 +173,137 @@ namespace {
                     }
             p.fine[(long long) g[0] + (long long) g[1] * p.fs1 + (long long) g[2] * p.fs2] += acc;
         }
+    }
+
+    // ---- table-driven transfer kernels (2-D / 3-D).  The per-axis index / weight logic of restrict_kernel and prolong_kernel above
+    // (parents, neighbours, wall and periodic handling) is evaluated ONCE per level on the host into small per-axis tables; the
+    // kernels then do nothing but table look-ups, 4 / 8 (prolong) or up to 16 / 64 (restrict) cached loads and the multiply-adds:
+    // no branches, no local-memory index arrays.  ncu (profiles/r2c_c4_launches.csv): level-0 prolongation 239 us -> HBM-bound.
+    struct AxisTab {
+        const int* pidx;   // [pn][2] coarse indices feeding fine index plo + q
+        const double* pw;  // [pn][2] their weights (0 where the tap does not exist)
+        const int* ridx;   // [rn][4] fine indices feeding coarse index rlo + q
+        const double* rw;  // [rn][4] their weights
+        int plo, pn, rlo, rn, rcnt;
+    };
+    struct XferTab {
+        AxisTab ax[3];
+    };
+    inline void host_prolong_axis(const XferParams& p, int d, int g, int idx[2], double w[2]) {
+        idx[0] = idx[1] = 0, w[0] = 1.0, w[1] = 0.0;
+        if (d >= p.dim) return;
+        const int r = g - p.f0[d];
+        const int par = p.c0[d] + (r >> 1);
+        if (p.center[d]) {
+            int nb = (r & 1) ? par + 1 : par - 1;
+            if (p.periodic[d] && !p.chalo[d]) {
+                if (nb < p.c0[d]) nb += p.cper[d];
+                else if (nb >= p.c0[d] + p.cper[d])
+                    nb -= p.cper[d];
+            }
+            idx[0] = par, w[0] = cc_weight(p, d, g, par);
+            idx[1] = nb, w[1] = cc_weight(p, d, g, nb);
+        } else if ((r & 1) == 0) {
+            idx[0] = idx[1] = par, w[0] = 1.0, w[1] = 0.0;
+        } else {
+            idx[0] = par, idx[1] = par + 1, w[0] = w[1] = 0.5;
+            if (p.periodic[d] && !p.chalo[d] && idx[1] >= p.c0[d] + p.cper[d]) idx[1] -= p.cper[d];
+        }
+        for (int a = 0; a < 2; ++a)
+            if (!p.chalo[d] && (idx[a] < p.clo[d] || idx[a] >= p.chi[d])) {// outside the coarse box: the tap does not exist
+                w[a] = 0.0;
+                idx[a] = idx[a] < p.clo[d] ? p.clo[d] : p.chi[d] - 1;
+            }
+    }
+    inline int host_restrict_axis(const XferParams& p, int d, int I, int idx[4], double w[4]) {
+        for (int a = 0; a < 4; ++a) idx[a] = 0, w[a] = 0.0;
+        if (d >= p.dim) {
+            w[0] = 1.0;
+            return 1;
+        }
+        const int cnt = p.center[d] ? 4 : 3;
+        for (int a = 0; a < cnt; ++a) {
+            int i = p.f0[d] + 2 * (I - p.c0[d]) - 1 + a;
+            if (p.periodic[d] && !p.fhalo[d]) {
+                if (i < p.f0[d]) i += p.fper[d];
+                else if (i >= p.f0[d] + p.fper[d])
+                    i -= p.fper[d];
+            }
+            idx[a] = i;
+            if (p.center[d]) w[a] = ((i >= p.flo[d] && i < p.fhi[d]) || (p.periodic[d] && p.fhalo[d])) ? 0.5 * cc_weight(p, d, i, I) : 0.0;
+            else
+                w[a] = a == 1 ? 0.5 : 0.25;
+            if (!p.fhalo[d] && (i < p.flo[d] || i >= p.fhi[d])) {
+                w[a] = 0.0;
+                idx[a] = i < p.flo[d] ? p.flo[d] : p.fhi[d] - 1;
+            }
+        }
+        for (int a = cnt; a < 4; ++a) idx[a] = idx[cnt - 1];// unused tap: weight 0, a valid address
+        return cnt;
+    }
+
+    template <int DIM>
+    __global__ void __launch_bounds__(256) prolong_fast_kernel(double* __restrict__ fine, long long fs1, long long fs2, const double* __restrict__ coarse,
+                                                               long long cs1, long long cs2, opf::LaunchRange w, const __grid_constant__ XferTab t) {
+        const int i = w.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= w.hi[0]) return;
+        const int j = w.lo[1] + (int) blockIdx.y, k = w.lo[2] + (int) blockIdx.z;
+        const int qx = 2 * (i - t.ax[0].plo), qy = 2 * (j - t.ax[1].plo);
+        const int ix0 = t.ax[0].pidx[qx], ix1 = t.ax[0].pidx[qx + 1];
+        const double wx0 = t.ax[0].pw[qx], wx1 = t.ax[0].pw[qx + 1];
+        const long long jy0 = (long long) t.ax[1].pidx[qy] * cs1, jy1 = (long long) t.ax[1].pidx[qy + 1] * cs1;
+        const double wy0 = t.ax[1].pw[qy], wy1 = t.ax[1].pw[qy + 1];
+        double acc;
+        if constexpr (DIM == 2) {
+            acc = wy0 * (wx0 * __ldg(coarse + ix0 + jy0) + wx1 * __ldg(coarse + ix1 + jy0)) + wy1 * (wx0 * __ldg(coarse + ix0 + jy1) + wx1 * __ldg(coarse + ix1 + jy1));
+        } else {
+            const int qz = 2 * (k - t.ax[2].plo);
+            const long long kz0 = (long long) t.ax[2].pidx[qz] * cs2, kz1 = (long long) t.ax[2].pidx[qz + 1] * cs2;
+            const double wz0 = t.ax[2].pw[qz], wz1 = t.ax[2].pw[qz + 1];
+            const double a0 = wy0 * (wx0 * __ldg(coarse + ix0 + jy0 + kz0) + wx1 * __ldg(coarse + ix1 + jy0 + kz0))
+                              + wy1 * (wx0 * __ldg(coarse + ix0 + jy1 + kz0) + wx1 * __ldg(coarse + ix1 + jy1 + kz0));
+            const double a1 = wy0 * (wx0 * __ldg(coarse + ix0 + jy0 + kz1) + wx1 * __ldg(coarse + ix1 + jy0 + kz1))
+                              + wy1 * (wx0 * __ldg(coarse + ix0 + jy1 + kz1) + wx1 * __ldg(coarse + ix1 + jy1 + kz1));
+            acc = wz0 * a0 + wz1 * a1;
+        }
+        const long long o = (long long) i + (long long) j * fs1 + (long long) k * fs2;
+        fine[o] += acc;
+    }
+    template <int DIM>
+    __global__ void __launch_bounds__(256) restrict_fast_kernel(const double* __restrict__ fine, long long fs1, long long fs2, double* __restrict__ coarse,
+                                                                long long cs1, long long cs2, opf::LaunchRange w, const __grid_constant__ XferTab t) {
+        const int I = w.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+        if (I >= w.hi[0]) return;
+        const int J = w.lo[1] + (int) blockIdx.y, K = w.lo[2] + (int) blockIdx.z;
+        const int qx = 4 * (I - t.ax[0].rlo), qy = 4 * (J - t.ax[1].rlo);
+        int ix[4];
+        double wx[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ix[a] = t.ax[0].ridx[qx + a], wx[a] = t.ax[0].rw[qx + a];
+        double acc = 0.0;
+        if constexpr (DIM == 2) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double wy = t.ax[1].rw[qy + b];
+                const double* row = fine + (long long) t.ax[1].ridx[qy + b] * fs1;
+                acc += wy * (wx[0] * __ldg(row + ix[0]) + wx[1] * __ldg(row + ix[1]) + wx[2] * __ldg(row + ix[2]) + wx[3] * __ldg(row + ix[3]));
+            }
+        } else {
+            const int qz = 4 * (K - t.ax[2].rlo);
+            for (int c = 0; c < t.ax[2].rcnt; ++c) {
+                const double wz = t.ax[2].rw[qz + c];
+                const double* pl = fine + (long long) t.ax[2].ridx[qz + c] * fs2;
+                double accp = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double wy = t.ax[1].rw[qy + b];
+                    const double* row = pl + (long long) t.ax[1].ridx[qy + b] * fs1;
+                    accp += wy * (wx[0] * __ldg(row + ix[0]) + wx[1] * __ldg(row + ix[1]) + wx[2] * __ldg(row + ix[2]) + wx[3] * __ldg(row + ix[3]));
+                }
+                acc += wz * accp;
+            }
+        }
+        coarse[(long long) I + (long long) J * cs1 + (long long) K * cs2] = acc;
     }
 
     // probe vector for the diagonal: 1 on the cells whose index is congruent to `col` modulo m on every axis
@@ -308,6 +439,10 @@ struct opf_solver_s {
         bool dist = false;  // fields are slab/block-decomposed like the target (halo exchange in updatePadding, global reductions)
         bool owns_pin = true;// the first assignable cell lies in w
         long long pin_off = 0;// first assignable cell of this level (pinned on every level when the problem is pinned)
+        // transfer tables between this level and the next coarser one (built on first use)
+        XferTab tab{};
+        void* tab_mem = nullptr;
+        bool tab_ready = false;
     };
     opf_field_s* target = nullptr;
     std::string lhs_sig, res_sig, smooth_sig;
@@ -505,6 +640,53 @@ namespace {
         return p;
     }
 
+
+    // host evaluation of the per-axis transfer stencils into device tables covering the whole storage range of both levels
+    int build_xfer_tab(Solver* s, int lf) {
+        auto &Lf = s->lv[lf], &Lc = s->lv[lf + 1];
+        if (Lf.tab_ready) return OPF_OK;
+        const XferParams p = xfer(s, lf);
+        std::vector<int> ib;
+        std::vector<double> wb;
+        size_t ioff[3][2], woff[3][2];
+        for (int d = 0; d < 3; ++d) {
+            AxisTab& a = Lf.tab.ax[d];
+            const bool used = d < p.dim;
+            a.plo = used ? Lf.x->storage.start[d] : 0;
+            a.pn = used ? Lf.x->storage.end[d] - Lf.x->storage.start[d] : 1;
+            a.rlo = used ? Lc.x->storage.start[d] : 0;
+            a.rn = used ? Lc.x->storage.end[d] - Lc.x->storage.start[d] : 1;
+            a.rcnt = used ? (p.center[d] ? 4 : 3) : 1;
+            ioff[d][0] = ib.size(), woff[d][0] = wb.size();
+            for (int q = 0; q < a.pn; ++q) {
+                int idx[2];
+                double w[2];
+                host_prolong_axis(p, d, a.plo + q, idx, w);
+                ib.push_back(idx[0]), ib.push_back(idx[1]), wb.push_back(w[0]), wb.push_back(w[1]);
+            }
+            ioff[d][1] = ib.size(), woff[d][1] = wb.size();
+            for (int q = 0; q < a.rn; ++q) {
+                int idx[4];
+                double w[4];
+                host_restrict_axis(p, d, a.rlo + q, idx, w);
+                for (int t = 0; t < 4; ++t) ib.push_back(idx[t]), wb.push_back(w[t]);
+            }
+        }
+        const size_t wbytes = wb.size() * sizeof(double), ibytes = ib.size() * sizeof(int);
+        OPF_CUDA(cudaMalloc(&Lf.tab_mem, wbytes + ibytes));
+        OPF_CUDA(cudaMemcpy(Lf.tab_mem, wb.data(), wbytes, cudaMemcpyHostToDevice));
+        OPF_CUDA(cudaMemcpy((char*) Lf.tab_mem + wbytes, ib.data(), ibytes, cudaMemcpyHostToDevice));
+        const double* wd = (const double*) Lf.tab_mem;
+        const int* id = (const int*) ((char*) Lf.tab_mem + wbytes);
+        for (int d = 0; d < 3; ++d) {
+            AxisTab& a = Lf.tab.ax[d];
+            a.pidx = id + ioff[d][0], a.pw = wd + woff[d][0];
+            a.ridx = id + ioff[d][1], a.rw = wd + woff[d][1];
+        }
+        Lf.tab_ready = true;
+        return OPF_OK;
+    }
+
     // singular operators (the caller pinned a value: all-Neumann / periodic): keep every level's right-hand side in the
     // range of the operator by removing its mean -- on the device, no host round trip
     int project_mean(Solver* s, opf_field_s* f, const Range& w, const Range& g, bool dist) {
@@ -522,7 +704,12 @@ namespace {
     int vcycle(Solver* s, int level, bool zero_guess, bool top_is_mean_free = false) {
         auto& L = s->lv[level];
         const int last = (int) s->lv.size() - 1;
-        if (s->singular && !top_is_mean_free)
+        // Coarse right-hand sides are restrictions of a mean-free residual by an operator whose columns all sum to 2^-dim (R = P^T / 2^dim,
+        // P interpolates constants exactly on all-Neumann / periodic problems): mean-free again up to rounding, and nothing accumulates
+        // because every cycle starts from the Krylov residual.  Their projection passes (3 launches per level per cycle) are off by
+        // default; OPF_MG_PROJECT_COARSE=1 restores them.
+        static const int project_coarse = getenv("OPF_MG_PROJECT_COARSE") ? atoi(getenv("OPF_MG_PROJECT_COARSE")) : 0;
+        if (s->singular && !top_is_mean_free && (level == 0 || project_coarse))
             if (int rc = project_mean(s, L.b, L.w, L.g, L.dist)) return rc;
         static const int coarse_sweeps = getenv("OPF_MG_COARSE_SWEEPS") ? atoi(getenv("OPF_MG_COARSE_SWEEPS")) : 8;
         if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : coarse_sweeps, zero_guess);
@@ -547,8 +734,16 @@ namespace {
             OPF_CUDA(cudaMemsetAsync(C.b->buf[C.b->cur], 0, sizeof(double) * C.b->elems, ctx().stream));
         }
         for (int d = 0; d < 3; ++d) p.wlo[d] = cw.start[d], p.whi[d] = cw.end[d];
+        static const int fast_xfer = getenv("OPF_MG_FAST_XFER") ? atoi(getenv("OPF_MG_FAST_XFER")) : 1;
+        const bool fast = fast_xfer && p.dim >= 2;
+        if (fast)
+            if (int rc = build_xfer_tab(s, level)) return rc;
         if (cw.count() > 0) {
-            restrict_kernel<<<box_grid(cw).grid, box_grid(cw).block, 0, ctx().stream>>>(p);
+            if (fast && p.dim == 2) restrict_fast_kernel<2><<<box_grid(cw).grid, box_grid(cw).block, 0, ctx().stream>>>(p.fine, p.fs1, p.fs2, p.coarse, p.cs1, p.cs2, lr_of(cw), L.tab);
+            else if (fast)
+                restrict_fast_kernel<3><<<box_grid(cw).grid, box_grid(cw).block, 0, ctx().stream>>>(p.fine, p.fs1, p.fs2, p.coarse, p.cs1, p.cs2, lr_of(cw), L.tab);
+            else
+                restrict_kernel<<<box_grid(cw).grid, box_grid(cw).block, 0, ctx().stream>>>(p);
             ctx().launches++;
         }
         if (L.dist && !C.dist)
@@ -560,7 +755,11 @@ namespace {
         p.fine = L.x->biased(L.x->cur), p.fs1 = L.x->pitch1, p.fs2 = L.x->pitch2;
         p.coarse = C.x->biased(C.x->cur), p.cs1 = C.x->pitch1, p.cs2 = C.x->pitch2;
         for (int d = 0; d < 3; ++d) p.wlo[d] = L.w.start[d], p.whi[d] = L.w.end[d];
-        prolong_kernel<<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p);
+        if (fast && p.dim == 2) prolong_fast_kernel<2><<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p.fine, p.fs1, p.fs2, p.coarse, p.cs1, p.cs2, lr_of(L.w), L.tab);
+        else if (fast)
+            prolong_fast_kernel<3><<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p.fine, p.fs1, p.fs2, p.coarse, p.cs1, p.cs2, lr_of(L.w), L.tab);
+        else
+            prolong_kernel<<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
         return smooth(s, level, post, false);
@@ -777,6 +976,9 @@ namespace {
     }
 
     void free_level_fields(Solver::Level& L) {
+        if (L.tab_mem) cudaFree(L.tab_mem);
+        L.tab_mem = nullptr;
+        L.tab_ready = false;
         for (opf_field_s* f : {L.x, L.b, L.r, L.q, L.dinv})
             if (f) opf_field_destroy(f);
     }

@@ -67,6 +67,7 @@ def test_host_assign_other_destination(engine):
     lr = u.localRange
     a = np.asfortranarray(np.random.default_rng(5).standard_normal(lr.shape(3)))
     ur.upload_raw(a.ctypes.data, lr)
+    ur.updatePadding()
     vr.assign(lap(ur, 3))
     sig, fields, scalars = lap(u, 3).flatten()
     F = (C.c_void_p * len(fields))(*[f.h for f in fields])
