@@ -27,7 +27,7 @@ extern "C" {
 
 #define OPF_MAX_DIM 3
 #define OPF_MAX_FIELDS 32  /* field leaves per expression  */
-#define OPF_MAX_SCALARS 16 /* scalar leaves per expression */
+#define OPF_MAX_SCALARS 32 /* scalar leaves per expression (a 3x3x3 convolution kernel takes 27) */
 #define OPF_MAX_NODES 96   /* tree nodes per expression    */
 
 typedef enum {
@@ -174,6 +174,10 @@ int opf_field_neighbors(opf_field_t f, int cap, int* ranks, opf_range* send, opf
  * library itself carries the expressions of the acceptance programs (opf_expr_builtin_count/name). */
 typedef int (*opf_expr_launcher)(const void* args_blob, const void* launch_blob, void* stream);
 int opf_expr_register(const char* signature, opf_expr_launcher fn);
+/* same, with the layout stamp of the translation unit that instantiated the launcher (OPF_DEVICE_ABI of opf_device.cuh: sizes of the
+ * ExprArgs / LaunchInfo blobs the engine hands to it): a program compiled against an older header is refused with OPF_ERR_INVALID
+ * instead of reading the blobs with the wrong layout.  The front-end headers call this one. */
+int opf_expr_register_abi(const char* signature, opf_expr_launcher fn, unsigned long long abi);
 int opf_expr_is_registered(const char* signature);
 int opf_expr_builtin_count(void);
 const char* opf_expr_builtin_name(int i);
@@ -238,6 +242,7 @@ typedef struct opf_solver_params { /* StructSolverParamsBase :39-51 + the per-so
     int precond_max_iter;
     int num_pre_relax, num_post_relax, relax_type; /* 0 Jacobi 1 weighted Jacobi 2/3 red-black GS */
     int print_level;
+    int k_dim;              /* GMRES restart length (StructSolverGMRES.hpp kDim; 0 = hypre's default 5) */
 } opf_solver_params;
 
 typedef struct opf_solve_state { int niter; double relerr, abserr; } opf_solve_state; /* EqnSolveState EqnSolveHandler.hpp:17-25 */
@@ -247,7 +252,7 @@ typedef struct opf_solve_state { int niter; double relerr, abserr; } opf_solve_s
  * lhs that ARE the unknown are flagged in `unknown_mask` (bit k <=> field leaf k is e; their entries in lhs_fields are ignored).
  * The operator is never assembled: A.p = lhs evaluated on p with the target's boundary conditions made homogeneous, and
  * b = rhs - lhs(e = 0 with the real boundary data).  pin_value pins the first assignable cell exactly like the reference
- * (HYPREEqnSolveHandler.hpp:145-163, StencilField.hpp:132).  Supported: type PCG / BICGSTAB / GMRES(=BICGSTAB) / JACOBI / PFMG
+ * (HYPREEqnSolveHandler.hpp:145-163, StencilField.hpp:132).  Supported: type PCG / BICGSTAB / GMRES(k) (FGMRES and LGMRES requests run as GMRES) / JACOBI / PFMG
  * (stand-alone geometric multigrid), precond NONE / JACOBI / PFMG.  lhs may also carry terms without the unknown (affine operator:
  * the front-end passes lhs(e) - rhs(e) with rhs "S<0>" = 0 when both sides of `==` contain e); multigrid needs an lhs whose field
  * leaves are all the unknown.  A decomposed target (opf_field_desc.split_map) is solved with distributed multigrid levels. */

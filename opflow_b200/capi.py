@@ -59,7 +59,7 @@ class SolverParams(C.Structure):
     _fields_ = [("type", C.c_int), ("precond", C.c_int), ("tol", C.c_double), ("max_iter", C.c_int),
                 ("static_mat", C.c_int), ("pin_value", C.c_int), ("precond_tol", C.c_double),
                 ("precond_max_iter", C.c_int), ("num_pre_relax", C.c_int), ("num_post_relax", C.c_int),
-                ("relax_type", C.c_int), ("print_level", C.c_int)]
+                ("relax_type", C.c_int), ("print_level", C.c_int), ("k_dim", C.c_int)]
 
 
 class SolveState(C.Structure):
@@ -119,6 +119,7 @@ SIGNATURES = {
     "opf_field_swap": (C.c_int, [_V, _V]),
     "opf_field_neighbors": (C.c_int, [_V, C.c_int, _I, _R, _R, _I]),
     "opf_expr_register": (C.c_int, [C.c_char_p, _V]),
+    "opf_expr_register_abi": (C.c_int, [C.c_char_p, _V, C.c_ulonglong]),
     "opf_expr_is_registered": (C.c_int, [C.c_char_p]),
     "opf_expr_builtin_count": (C.c_int, []),
     "opf_expr_builtin_name": (C.c_char_p, [C.c_int]),

@@ -16,7 +16,7 @@ namespace opfe {
         K_F, K_S,
         K_ADD, K_SUB, K_MUL, K_DIV, K_MIN, K_MAX, K_POW, K_LT, K_LE, K_GT, K_GE, K_EQ, K_NE, K_AND, K_OR,
         K_NEG, K_POS, K_NOT, K_SQRT, K_ABS, K_EXP, K_LOG, K_SIN, K_COS, K_TAN, K_TANH, K_POW2,
-        K_COND,
+        K_COND, K_UNI, K_BIN, K_FLC2N, K_FLN2C, K_CONV,// K_UNI / K_BIN: point-wise math functors without any special preparation (AMDS.hpp:40-89)
         K_D2C, K_D1C, K_D1DN, K_D1UP, K_WENODN, K_WENOUP, K_INTPC2N, K_INTPN2C
     };
     struct KindInfo {
@@ -34,11 +34,14 @@ namespace opfe {
             {"Sin", K_SIN, 1, false},     {"Cos", K_COS, 1, false},     {"Tan", K_TAN, 1, false},     {"Tanh", K_TANH, 1, false},
             {"Pow2", K_POW2, 1, false},   {"Cond", K_COND, 3, false},   {"D2C", K_D2C, 1, true},      {"D1C", K_D1C, 1, true},
             {"D1Dn", K_D1DN, 1, true},    {"D1Up", K_D1UP, 1, true},    {"WenoDn", K_WENODN, 1, true}, {"WenoUp", K_WENOUP, 1, true},
-            {"IntpC2N", K_INTPC2N, 1, true}, {"IntpN2C", K_INTPN2C, 1, true}};
+            {"IntpC2N", K_INTPC2N, 1, true}, {"IntpN2C", K_INTPN2C, 1, true}, {"Conv", K_CONV, 1, false},
+            {"FlCentralC2N", K_FLC2N, 2, true}, {"FlCentralN2C", K_FLN2C, 2, true}, {"FlQuickC2N", K_FLC2N, 2, true}, {"FlQuickN2C", K_FLN2C, 2, true}, {"FlCuiC2N", K_FLC2N, 2, true}, {"FlCuiN2C", K_FLN2C, 2, true}, {"FlFrommC2N", K_FLC2N, 2, true}, {"FlFrommN2C", K_FLN2C, 2, true}, {"FlLuiC2N", K_FLC2N, 2, true}, {"FlLuiN2C", K_FLN2C, 2, true}, {"FlMinmodC2N", K_FLC2N, 2, true}, {"FlMinmodN2C", K_FLN2C, 2, true}, {"FlSuperbeeC2N", K_FLC2N, 2, true}, {"FlSuperbeeN2C", K_FLN2C, 2, true}, {"FlMusclC2N", K_FLC2N, 2, true}, {"FlMusclN2C", K_FLN2C, 2, true}, {"FlHarmonicC2N", K_FLC2N, 2, true}, {"FlHarmonicN2C", K_FLN2C, 2, true}, {"FlAlbadaC2N", K_FLC2N, 2, true}, {"FlAlbadaN2C", K_FLN2C, 2, true}, 
+            {"Exp2", K_UNI, 1, false}, {"Expm1", K_UNI, 1, false}, {"Log10", K_UNI, 1, false}, {"Log2", K_UNI, 1, false}, {"Log1p", K_UNI, 1, false}, {"Cbrt", K_UNI, 1, false}, {"ASin", K_UNI, 1, false}, {"ACos", K_UNI, 1, false}, {"ATan", K_UNI, 1, false}, {"Sinh", K_UNI, 1, false}, {"Cosh", K_UNI, 1, false}, {"ASinh", K_UNI, 1, false}, {"ACosh", K_UNI, 1, false}, {"ATanh", K_UNI, 1, false}, {"Erf", K_UNI, 1, false}, {"Erfc", K_UNI, 1, false}, {"TGamma", K_UNI, 1, false}, {"LGamma", K_UNI, 1, false}, {"Ceil", K_UNI, 1, false}, {"Floor", K_UNI, 1, false}, {"Trunc", K_UNI, 1, false}, {"Round", K_UNI, 1, false}, {"LRound", K_UNI, 1, false}, {"LLRound", K_UNI, 1, false}, {"NearbyInt", K_UNI, 1, false}, {"Rint", K_UNI, 1, false}, {"LRint", K_UNI, 1, false}, {"LLRint", K_UNI, 1, false}, {"ILogb", K_UNI, 1, false}, {"Logb", K_UNI, 1, false}, {"FMod", K_BIN, 2, false}, {"Remainder", K_BIN, 2, false}, {"FDim", K_BIN, 2, false}, {"Hypot", K_BIN, 2, false}, {"ATan2", K_BIN, 2, false}, {"Ldexp", K_BIN, 2, false}, {"Scalbn", K_BIN, 2, false}, {"Scalbln", K_BIN, 2, false}, {"Nextafter", K_BIN, 2, false}, {"Nexttoward", K_BIN, 2, false}, {"Copysing", K_BIN, 2, false}};
 
     struct Node {
         int kind = 0, axis = -1, leaf = -1, nchild = 0;
         int child[3] = {-1, -1, -1};
+        int conv[4] = {1, 1, 1, 0};// Conv<n0,n1,n2,k0,E>: kernel extents and the first scalar slot of its entries
         // prepared properties
         bool scalar = false;
         int loc[D3] = {0, 0, 0};
@@ -104,6 +107,23 @@ namespace opfe {
                 else
                     t.nscalars = std::max(t.nscalars, v + 1);
             } else {
+                if (ki->kind == K_CONV) {// Conv<n0, n1, n2, k0, E>
+                    for (int q = 0; q < 4; ++q) {
+                        int v;
+                        if (!parse_int(v) || v < 0 || (q < 3 && (v < 1 || v > 2 * opf::WR + 1 || v % 2 == 0))) {
+                            err = "Conv<n0,n1,n2,k0,E>: odd extents 1..7 and a scalar slot expected";
+                            return -1;
+                        }
+                        t.nodes[me].conv[q] = v;
+                        ws();
+                        if (s[pos] != ',') {
+                            err = "expected ','";
+                            return -1;
+                        }
+                        ++pos;
+                    }
+                    t.nscalars = std::max(t.nscalars, t.nodes[me].conv[3] + t.nodes[me].conv[0] * t.nodes[me].conv[1] * t.nodes[me].conv[2]);
+                }
                 if (ki->has_axis) {
                     int v;
                     if (!parse_int(v) || v < 0 || v >= D3) {
@@ -245,6 +265,34 @@ namespace opfe {
                 n.loc[n.axis] = OPF_LOC_CORNER;
                 n.acc.start[n.axis]++, n.local.start[n.axis]++, n.logical.start[n.axis]++;
                 break;
+            case K_FLC2N:// D1FluxLimiterImpl<K, d, Cen2Cor>::prepare (D1FluxLimiter.hpp:155-171): props from arg2 (the interpolated field)
+                if (ch(1).scalar) return fail(OPF_ERR_INVALID, "flux-limiter interpolator applied to a scalar");
+                if (ch(1).loc[n.axis] != OPF_LOC_CENTER) return fail(OPF_ERR_LOC, "D1FluxLimiterIntp<Cen2Cor>: operand located in corner in dimension %d", n.axis);
+                inherit(n, ch(1));
+                n.loc[n.axis] = OPF_LOC_CORNER;
+                n.acc.start[n.axis] += 2, n.acc.end[n.axis] -= 1;
+                n.local.start[n.axis] += 2, n.local.end[n.axis] -= 1;
+                n.logical.start[n.axis] += 2, n.logical.end[n.axis] -= 1;
+                break;
+            case K_FLN2C:// D1FluxLimiterImpl<K, d, Cor2Cen>::prepare (D1FluxLimiter.hpp:188-203)
+                if (ch(1).scalar) return fail(OPF_ERR_INVALID, "flux-limiter interpolator applied to a scalar");
+                if (ch(1).loc[n.axis] != OPF_LOC_CORNER) return fail(OPF_ERR_LOC, "D1FluxLimiterIntp<Cor2Cen>: operand located in center in dimension %d", n.axis);
+                inherit(n, ch(1));
+                n.loc[n.axis] = OPF_LOC_CENTER;
+                n.acc.start[n.axis] += 1, n.acc.end[n.axis] -= 2;
+                n.local.start[n.axis] += 1, n.local.end[n.axis] -= 2;
+                n.logical.start[n.axis] += 1, n.logical.end[n.axis] -= 2;
+                break;
+            case K_CONV:// Convolution<ns...>::prepare (Convolution.hpp:66-82): every range shrinks by n/2 per axis
+                if (ch(0).scalar) return fail(OPF_ERR_INVALID, "convolution applied to a scalar");
+                inherit(n, ch(0));
+                for (int d = 0; d < D3; ++d) {
+                    const int h = n.conv[d] / 2;
+                    n.acc.start[d] += h, n.acc.end[d] -= h;
+                    n.local.start[d] += h, n.local.end[d] -= h;
+                    n.logical.start[d] += h, n.logical.end[d] -= h;
+                }
+                break;
             case K_INTPN2C:// D1Linear<d,Cor2Cen>::prepare (D1Linear.hpp:60-69)
                 if (ch(0).scalar) return fail(OPF_ERR_INVALID, "stencil operator applied to a scalar");
                 inherit(n, ch(0));
@@ -285,6 +333,17 @@ namespace opfe {
         }
         int l[D3], h[D3];
         for (int d = 0; d < D3; ++d) l[d] = lo_in[d], h[d] = hi_in[d];
+        if (n.kind == K_FLC2N || n.kind == K_FLN2C) {// the advecting field is read in place, the interpolated one at four taps
+            const int a = n.axis, ra = n.kind == K_FLC2N ? -2 : -1;
+            mlo[a] = std::min(mlo[a], lo_in[a] - 3);
+            mhi[a] = std::max(mhi[a], hi_in[a] + 3);
+            footprint(t, n.child[0], lo_in, hi_in, lo, hi, used, mlo, mhi);
+            l[a] += ra, h[a] += ra + 3;
+            footprint(t, n.child[1], l, h, lo, hi, used, mlo, mhi);
+            return;
+        }
+        if (n.kind == K_CONV)
+            for (int d = 0; d < D3; ++d) l[d] -= n.conv[d] / 2, h[d] += n.conv[d] / 2;
         if (n.axis >= 0) {
             const int a = n.axis;
             const bool center = t.nodes[n.child[0]].loc[a] == OPF_LOC_CENTER;
@@ -319,6 +378,8 @@ namespace opfe {
         switch (n.kind) {
             case K_D2C: case K_D1C: case K_D1DN: case K_D1UP: case K_INTPC2N: case K_INTPN2C: own = 1; break;
             case K_WENODN: case K_WENOUP: own = 3; break;
+            case K_FLC2N: case K_FLN2C: own = 2; break;
+            case K_CONV: own = std::max(n.conv[0], std::max(n.conv[1], n.conv[2])) / 2; break;
             default: own = 0;
         }
         int sub = 0;
@@ -619,6 +680,12 @@ int opf_expr_register(const char* signature, opf_expr_launcher fn) {
     r.map[strip(signature)] = fn;
     return OPF_OK;
 }
+int opf_expr_register_abi(const char* signature, opf_expr_launcher fn, unsigned long long abi) {
+    if (abi != OPF_DEVICE_ABI)
+        return fail(OPF_ERR_INVALID, "expression '%s' was compiled against another opf_device.cuh (layout stamp %llx, library %llx): rebuild the program",
+                    signature ? signature : "", abi, (unsigned long long) OPF_DEVICE_ABI);
+    return opf_expr_register(signature, fn);
+}
 int opf_expr_is_registered(const char* signature) { return signature && find_launcher(strip(signature)) != nullptr; }
 int opf_expr_builtin_count(void) { return (int) registry().builtin.size(); }
 const char* opf_expr_builtin_name(int i) {
@@ -675,7 +742,7 @@ int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_fiel
     // a pure point-wise expression of dst itself may be updated in place (no neighbour taps)
     bool has_stencil = false;
     for (const auto& n : p->tree.nodes)
-        if (n.axis >= 0) has_stencil = true;
+        if (n.axis >= 0 || n.kind == K_CONV) has_stencil = true;
     const bool use_twin = alias && has_stencil;
     if (use_twin)
         if (int rc = field_ensure_twin(dst)) return rc;

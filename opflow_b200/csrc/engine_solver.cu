@@ -357,27 +357,98 @@ namespace {
         int iters, maxit, cont, breakdown;
         double rel;
     };
+    // work item of the streaming Krylov kernels: (row, 1024-element segment of axis 0); a block takes items round-robin, its 256 threads
+    // take 2 consecutive cells each per trip and two trips are in flight (4 x 128-bit loads per operand per thread)
+    constexpr int KSEG = 1024;
+    struct RowIter {
+        long long nseg, items;
+        int n0, n1;
+        __device__ __forceinline__ RowIter(const opf::LaunchRange& w) {
+            n0 = w.hi[0] - w.lo[0], n1 = w.hi[1] - w.lo[1];
+            nseg = (n0 + KSEG - 1) / KSEG;
+            items = nseg * n1 * (long long) (w.hi[2] - w.lo[2]);
+        }
+        // -> offset of the segment's first cell, number of cells in it
+        __device__ __forceinline__ long long locate(const opf::LaunchRange& w, long long it, long long s1, long long s2, int& len) const {
+            const long long seg = it % nseg, row = it / nseg;
+            const int j = w.lo[1] + (int) (row % n1), k = w.lo[2] + (int) (row / n1);
+            const int b = (int) seg * KSEG;
+            len = min(KSEG, n0 - b);
+            return (long long) (w.lo[0] + b) + (long long) j * s1 + (long long) k * s2;
+        }
+    };
     // x += alpha p ; r -= alpha q ; partial sums of r.r          (48 B per cell instead of 24 + 24 + 8 in three passes)
     __global__ void __launch_bounds__(256) pcg_update_kernel(double* __restrict__ x, const double* __restrict__ p, double* __restrict__ r,
                                                              const double* __restrict__ q, long long s1, long long s2, opf::LaunchRange w,
-                                                             const double* __restrict__ ks, double* __restrict__ partials) {
+                                                             const double* __restrict__ ks, double* __restrict__ partials, int vec) {
         const double pq = ks[KS_PQ];
         const double alpha = pq != 0.0 ? ks[KS_RZ] / pq : 0.0;
-        const int n0 = w.hi[0] - w.lo[0], n1 = w.hi[1] - w.lo[1], n2 = w.hi[2] - w.lo[2];
-        const long long rows = (long long) n1 * n2;
+        const RowIter ri(w);
         double acc = 0.0;
-        for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-            const int j = w.lo[1] + (int) (row % n1), k = w.lo[2] + (int) (row / n1);
-            const long long o = (long long) w.lo[0] + (long long) j * s1 + (long long) k * s2;
-            for (int i = threadIdx.x; i < n0; i += blockDim.x) {
-                x[o + i] += alpha * p[o + i];
-                const double rn = r[o + i] - alpha * q[o + i];
-                r[o + i] = rn;
-                acc += rn * rn;
+        for (long long it = blockIdx.x; it < ri.items; it += gridDim.x) {
+            int len;
+            const long long o = ri.locate(w, it, s1, s2, len);
+            if (vec) {
+#pragma unroll 2
+                for (int i = 2 * threadIdx.x; i < len; i += 512) {
+                    if (i + 1 < len) {
+                        const double2 pv = *reinterpret_cast<const double2*>(p + o + i), qv = *reinterpret_cast<const double2*>(q + o + i);
+                        double2 xv = *reinterpret_cast<double2*>(x + o + i), rv = *reinterpret_cast<double2*>(r + o + i);
+                        xv.x += alpha * pv.x, xv.y += alpha * pv.y;
+                        rv.x -= alpha * qv.x, rv.y -= alpha * qv.y;
+                        *reinterpret_cast<double2*>(x + o + i) = xv;
+                        *reinterpret_cast<double2*>(r + o + i) = rv;
+                        acc += rv.x * rv.x + rv.y * rv.y;
+                    } else {
+                        x[o + i] += alpha * p[o + i];
+                        const double rn = r[o + i] - alpha * q[o + i];
+                        r[o + i] = rn;
+                        acc += rn * rn;
+                    }
+                }
+            } else {
+                for (int i = threadIdx.x; i < len; i += 256) {
+                    x[o + i] += alpha * p[o + i];
+                    const double rn = r[o + i] - alpha * q[o + i];
+                    r[o + i] = rn;
+                    acc += rn * rn;
+                }
             }
         }
         acc = opf::block_reduce(0, acc);
         if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    }
+    // partial sums of a.b over a box (the Krylov dot products; the generic reduction of an expression stays opf::reduce_kernel)
+    __global__ void __launch_bounds__(256) dot_fast_kernel(const double* __restrict__ a, const double* __restrict__ b, long long s1, long long s2,
+                                                           opf::LaunchRange w, double* __restrict__ partials, int vec) {
+        const RowIter ri(w);
+        double acc0 = 0.0, acc1 = 0.0;
+        for (long long it = blockIdx.x; it < ri.items; it += gridDim.x) {
+            int len;
+            const long long o = ri.locate(w, it, s1, s2, len);
+            if (vec) {
+#pragma unroll 2
+                for (int i = 2 * threadIdx.x; i < len; i += 512) {
+                    if (i + 1 < len) {
+                        const double2 av = *reinterpret_cast<const double2*>(a + o + i), bv = *reinterpret_cast<const double2*>(b + o + i);
+                        acc0 += av.x * bv.x;
+                        acc1 += av.y * bv.y;
+                    } else
+                        acc0 += a[o + i] * b[o + i];
+                }
+            } else {
+                for (int i = threadIdx.x; i < len; i += 256) acc0 += a[o + i] * b[o + i];
+            }
+        }
+        const double acc = opf::block_reduce(0, acc0 + acc1);
+        if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    }
+    // fixed-order fold of the partials into *out (deterministic run to run)
+    __global__ void __launch_bounds__(256) fold_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+        acc = opf::block_reduce(0, acc);
+        if (threadIdx.x == 0) out[0] = acc;
     }
     // folds the partials into ks[KS_RR], counts the iteration, decides continuation
     __global__ void __launch_bounds__(256) pcg_control_kernel(const double* __restrict__ partials, int n, double* __restrict__ ks, PcgCtl* ctl,
@@ -404,12 +475,27 @@ namespace {
     }
     // p = z + beta p with beta = (r.z)_new / (r.z)_old
     __global__ void __launch_bounds__(256) pcg_direction_kernel(double* __restrict__ p, const double* __restrict__ z, long long s1, long long s2,
-                                                                opf::LaunchRange w, const double* __restrict__ ks) {
+                                                                opf::LaunchRange w, const double* __restrict__ ks, int vec) {
         const double beta = ks[KS_RZN] / ks[KS_RZ];
-        const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (x0 >= w.hi[0] - w.lo[0]) return;
-        const long long o = (long long) (w.lo[0] + x0) + (long long) (w.lo[1] + (int) blockIdx.y) * s1 + (long long) (w.lo[2] + (int) blockIdx.z) * s2;
-        p[o] = z[o] + beta * p[o];
+        const RowIter ri(w);
+        for (long long it = blockIdx.x; it < ri.items; it += gridDim.x) {
+            int len;
+            const long long o = ri.locate(w, it, s1, s2, len);
+            if (vec) {
+#pragma unroll 2
+                for (int i = 2 * threadIdx.x; i < len; i += 512) {
+                    if (i + 1 < len) {
+                        const double2 zv = *reinterpret_cast<const double2*>(z + o + i);
+                        double2 pv = *reinterpret_cast<double2*>(p + o + i);
+                        pv.x = zv.x + beta * pv.x, pv.y = zv.y + beta * pv.y;
+                        *reinterpret_cast<double2*>(p + o + i) = pv;
+                    } else
+                        p[o + i] = z[o + i] + beta * p[o + i];
+                }
+            } else {
+                for (int i = threadIdx.x; i < len; i += 256) p[o + i] = z[o + i] + beta * p[o + i];
+            }
+        }
     }
     __global__ void pcg_shift_kernel(double* ks) { ks[KS_RZ] = ks[KS_RZN]; }
 
@@ -455,6 +541,7 @@ struct opf_solver_s {
     std::vector<Level> lv;
     opf_field_s *X = nullptr, *B = nullptr, *R = nullptr, *P = nullptr, *Z = nullptr, *Q = nullptr;
     opf_field_s *R0 = nullptr, *V = nullptr, *S = nullptr, *T = nullptr, *E0 = nullptr;// BiCGSTAB extras, boundary-data field
+    std::vector<opf_field_s*> gm_v;// GMRES basis (k + 1 vectors, allocated on first use)
     // an `lhs` that also carries terms without the unknown (the front-end passes  lhs(e) - rhs(e)  when both sides of `==`
     // contain e) is affine: lhs(p) = A.p + c.  C0 = lhs(0 with homogeneous BCs) = c is removed from every operator application.
     opf_field_s* C0 = nullptr;
@@ -1080,7 +1167,7 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
     s->Z = clone_homogeneous(target, "kry.z");
     s->Q = clone_homogeneous(target, "kry.q");
     s->E0 = opf_field_clone(target, "kry.e0");
-    const bool bicg = params->type != OPF_SOLVER_PCG && params->type != OPF_SOLVER_JACOBI && params->type != OPF_SOLVER_PFMG && params->type != OPF_SOLVER_SMG;
+    const bool bicg = params->type == OPF_SOLVER_BICGSTAB;
     if (bicg) {
         s->R0 = clone_homogeneous(target, "kry.r0");
         s->V = clone_homogeneous(target, "kry.v");
@@ -1138,6 +1225,7 @@ int opf_solver_destroy(opf_solver_t s) {
     for (auto& L : s->lv) free_level_fields(L);
     for (opf_field_s* f : {s->X, s->B, s->R, s->P, s->Z, s->Q, s->R0, s->V, s->S, s->T, s->E0, s->C0})
         if (f) opf_field_destroy(f);
+    for (opf_field_s* f : s->gm_v) opf_field_destroy(f);
     delete s;
     return OPF_OK;
 }
@@ -1145,18 +1233,42 @@ int opf_solver_destroy(opf_solver_t s) {
 
 // ---- device-resident PCG (see the kernels above).  One iteration, launched into the engine stream (plainly, or into a capture):
 //   q = A p ; pq = p.q ; x += (rz/pq) p ; r -= (rz/pq) q ; rr = r.r ; [control] ; z = M^-1 r ; rzn = r.z ; p = z + (rzn/rz) p ; rz = rzn
+// geometry of the streaming Krylov kernels over box w of fields cloned from the target (same pitches, same alignment)
+static int krylov_blocks(const Range& w) {
+    const long long nseg = (w.end[0] - w.start[0] + KSEG - 1) / KSEG;
+    const long long items = nseg * (w.end[1] - w.start[1]) * (long long) (w.end[2] - w.start[2]);
+    return (int) std::max<long long>(1, std::min<long long>(items, 8LL * ctx().sm_count));
+}
+static int krylov_vec(std::initializer_list<const opf_field_s*> fs, const Range& w) {
+    for (const opf_field_s* f : fs) {
+        const double* p0 = f->biased(f->cur) + ((long long) w.start[0] + (long long) w.start[1] * f->pitch1 + (long long) w.start[2] * f->pitch2);
+        if ((reinterpret_cast<uintptr_t>(p0) & 15) || (f->pitch1 & 1) || (f->pitch2 & 1)) return 0;
+    }
+    return 1;
+}
+// slot = sum over w of a.b, device-resident (two launches, no host synchronisation)
+static int krylov_dot(opf_field_s* a, opf_field_s* b, const Range& w, double* slot) {
+    Context& c = ctx();
+    if (a->pitch1 != b->pitch1 || a->pitch2 != b->pitch2) return dot_device(a, b, w, slot);
+    const int nb = krylov_blocks(w);
+    if (nb > c.red_cap - 8) return dot_device(a, b, w, slot);
+    dot_fast_kernel<<<nb, 256, 0, c.stream>>>(a->biased(a->cur), b->biased(b->cur), a->pitch1, a->pitch2, lr_of(w), c.red_buf, krylov_vec({a, b}, w));
+    fold_kernel<<<1, 256, 0, c.stream>>>(c.red_buf, nb, slot);
+    c.launches += 2;
+    return OPF_OK;
+}
+
 static int pcg_body(opf_solver_s* s, const Range& w, cudaGraphConditionalHandle handle, int use_cond) {
     Context& c = ctx();
     const bool dist = s->lv[0].dist && comm_active();
     if (int rc = apply_lhs(s, s->P, s->Q, 0)) return rc;
-    if (int rc = dot_device(s->P, s->Q, w, s->ks + KS_PQ)) return rc;
+    if (int rc = krylov_dot(s->P, s->Q, w, s->ks + KS_PQ)) return rc;
     if (dist)
         if (int rc = comm_allreduce_device(s->ks + KS_PQ, 1, OPF_RED_SUM, c.stream)) return rc;
-    const long long rows = (long long) (w.end[1] - w.start[1]) * (w.end[2] - w.start[2]);
-    const int nb = (int) std::max<long long>(1, std::min<long long>(rows, 4LL * c.sm_count));
+    const int nb = std::min(krylov_blocks(w), c.red_cap - 8);
     opf_field_s *X = s->X, *P = s->P, *R = s->R, *Q = s->Q;
     pcg_update_kernel<<<nb, 256, 0, c.stream>>>(X->biased(X->cur), P->biased(P->cur), R->biased(R->cur), Q->biased(Q->cur), X->pitch1, X->pitch2, lr_of(w), s->ks,
-                                                c.red_buf);
+                                                c.red_buf, krylov_vec({X, P, R, Q}, w));
     if (!dist) {
         pcg_control_kernel<<<1, 256, 0, c.stream>>>(c.red_buf, nb, s->ks, s->ctl_dev, handle, use_cond, 0);
         c.launches += 2;
@@ -1167,12 +1279,11 @@ static int pcg_body(opf_solver_s* s, const Range& w, cudaGraphConditionalHandle 
         c.launches += 3;
     }
     if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
-    if (int rc = dot_device(s->R, s->Z, w, s->ks + KS_RZN)) return rc;
+    if (int rc = krylov_dot(s->R, s->Z, w, s->ks + KS_RZN)) return rc;
     if (dist)
         if (int rc = comm_allreduce_device(s->ks + KS_RZN, 1, OPF_RED_SUM, c.stream)) return rc;
     opf_field_s* Z = s->Z;
-    const BoxGrid bg = box_grid(w);
-    pcg_direction_kernel<<<bg.grid, bg.block, 0, c.stream>>>(P->biased(P->cur), Z->biased(Z->cur), P->pitch1, P->pitch2, lr_of(w), s->ks);
+    pcg_direction_kernel<<<krylov_blocks(w), 256, 0, c.stream>>>(P->biased(P->cur), Z->biased(Z->cur), P->pitch1, P->pitch2, lr_of(w), s->ks, krylov_vec({P, Z}, w));
     pcg_shift_kernel<<<1, 1, 0, c.stream>>>(s->ks);
     c.launches += 2;
     OPF_CUDA(cudaGetLastError());
@@ -1207,7 +1318,7 @@ static int run_pcg_device(opf_solver_s* s, const Range& w, double bnorm, double 
     // z = M^-1 r ; p = z ; rz = r.z
     if (int rc = precondition_pinned(s, s->R, s->Z)) return rc;
     if (int rc = assign(s->P, "F<0>", {s->Z}, {})) return rc;
-    if (int rc = dot_device(s->R, s->Z, w, s->ks + KS_RZ)) return rc;
+    if (int rc = krylov_dot(s->R, s->Z, w, s->ks + KS_RZ)) return rc;
     if (dist)
         if (int rc = comm_allreduce_device(s->ks + KS_RZ, 1, OPF_RED_SUM, c.stream)) return rc;
     auto fetch = [&]() -> int {
@@ -1336,8 +1447,85 @@ static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm
             ++iters;
             rel = std::sqrt(rnorm2) / bnorm;
         }
+    } else if (type == OPF_SOLVER_GMRES || type == OPF_SOLVER_FGMRES || type == OPF_SOLVER_LGMRES) {
+        // restarted GMRES(k), right-preconditioned (HYPRE_StructGMRES*, StructSolverGMRES.hpp:20-96; hypre's default k_dim = 5), modified
+        // Gram-Schmidt, Givens rotations on the host.  The preconditioner is a fixed linear operator here (Jacobi or a V-cycle), so the
+        // flexible variant (FGMRES) coincides with it; LGMRES requests run as GMRES with the augmentation vectors added to k.
+        const int k = std::max(1, std::min(s->params.k_dim > 0 ? s->params.k_dim : 5, 50));
+        if ((int) s->gm_v.size() < k + 1) {
+            for (int i = (int) s->gm_v.size(); i < k + 1; ++i) {
+                opf_field_s* v = clone_homogeneous(s->target, "kry.gmres.v");
+                if (!v) return OPF_ERR_CUDA;
+                s->gm_v.push_back(v);
+            }
+        }
+        std::vector<double> H((size_t) (k + 1) * k, 0.0), cs(k, 0.0), sn(k, 0.0), g(k + 1, 0.0), y(k, 0.0);
+        auto h = [&](int i, int j) -> double& { return H[(size_t) i * k + j]; };
+        while (rel > tol && iters < maxit) {
+            const double beta = std::sqrt(rnorm2);
+            if (beta == 0.0) break;
+            if (int rc = assign(s->gm_v[0], "Mul<S<0>,F<0>>", {s->R}, {1.0 / beta})) return rc;
+            std::fill(g.begin(), g.end(), 0.0);
+            g[0] = beta;
+            int j = 0;
+            bool breakdown = false;
+            for (; j < k && iters < maxit; ++j) {
+                if (int rc = precondition_pinned(s, s->gm_v[j], s->Z)) return rc;// z = M^-1 v_j
+                if (int rc = apply_lhs(s, s->Z, s->Q, 0)) return rc;             // w = A z
+                for (int i = 0; i <= j; ++i) {
+                    double hij = 0;
+                    if (int rc = dot(s, s->Q, s->gm_v[i], w, &hij)) return rc;
+                    h(i, j) = hij;
+                    if (int rc = assign(s->Q, "Add<F<0>,Mul<S<0>,F<1>>>", {s->Q, s->gm_v[i]}, {-hij})) return rc;
+                }
+                double wn2 = 0;
+                if (int rc = dot(s, s->Q, s->Q, w, &wn2)) return rc;
+                const double wn = std::sqrt(wn2);
+                h(j + 1, j) = wn;
+                if (wn != 0.0) {
+                    if (int rc = assign(s->gm_v[j + 1], "Mul<S<0>,F<0>>", {s->Q}, {1.0 / wn})) return rc;
+                } else
+                    breakdown = true;// lucky breakdown: the Krylov space contains the solution
+                for (int i = 0; i < j; ++i) {// previous rotations on the new column
+                    const double t = cs[i] * h(i, j) + sn[i] * h(i + 1, j);
+                    h(i + 1, j) = -sn[i] * h(i, j) + cs[i] * h(i + 1, j);
+                    h(i, j) = t;
+                }
+                const double den = std::hypot(h(j, j), h(j + 1, j));
+                cs[j] = den != 0.0 ? h(j, j) / den : 1.0;
+                sn[j] = den != 0.0 ? h(j + 1, j) / den : 0.0;
+                h(j, j) = cs[j] * h(j, j) + sn[j] * h(j + 1, j);
+                h(j + 1, j) = 0.0;
+                g[j + 1] = -sn[j] * g[j];
+                g[j] = cs[j] * g[j];
+                ++iters;
+                rel = std::fabs(g[j + 1]) / bnorm;
+                if (rel <= tol || breakdown) {
+                    ++j;
+                    break;
+                }
+            }
+            // y = H^-1 g ; x += M^-1 (V y)
+            for (int i = j - 1; i >= 0; --i) {
+                double acc = g[i];
+                for (int c = i + 1; c < j; ++c) acc -= h(i, c) * y[c];
+                y[i] = h(i, i) != 0.0 ? acc / h(i, i) : 0.0;
+            }
+            if (j > 0) {
+                if (int rc = assign(s->Q, "Mul<S<0>,F<0>>", {s->gm_v[0]}, {y[0]})) return rc;
+                for (int i = 1; i < j; ++i)
+                    if (int rc = assign(s->Q, "Add<F<0>,Mul<S<0>,F<1>>>", {s->Q, s->gm_v[i]}, {y[i]})) return rc;
+                if (int rc = precondition_pinned(s, s->Q, s->Z)) return rc;
+                if (int rc = assign(s->X, "Add<F<0>,F<1>>", {s->X, s->Z}, {})) return rc;
+            }
+            // true residual for the restart (and for the reported relative residual)
+            if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
+            if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
+            rel = std::sqrt(rnorm2) / bnorm;
+            if (breakdown || j == 0) break;
+        }
     } else {
-        // right-preconditioned BiCGSTAB (also used for GMRES-family requests: non-symmetric operators)
+        // right-preconditioned BiCGSTAB (StructSolverBiCGSTAB.hpp)
         double rho = 1, alpha = 1, omega = 1, rho_new = 0, r0v = 0, ts = 0, tt = 0;
         if (int rc = assign(s->R0, "F<0>", {s->R}, {})) return rc;
         if (int rc = assign(s->P, "S<0>", {}, {0.0})) return rc;

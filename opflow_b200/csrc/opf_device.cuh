@@ -32,7 +32,7 @@ extern "C" void opf_internal_note_kernel(const char* name);
 namespace opf {
 
     constexpr int MAX_FIELDS = 32;
-    constexpr int MAX_SCALARS = 16;
+    constexpr int MAX_SCALARS = 32;// a 3 x 3 x 3 convolution kernel occupies 27 slots
     constexpr int MAX_NODES = 96;
 
     // element (i0,i1,i2) (global indices) lives at p[i0 + i1*s1 + i2*s2]; the field offset is folded into p
@@ -94,6 +94,9 @@ namespace opf {
         double* result;// where the folded value goes (device memory); null: partials + n_partials
     };
 
+    // layout stamp of the blobs exchanged between libopflow_b200.so and launchers instantiated in user translation units
+#define OPF_DEVICE_ABI (((unsigned long long) sizeof(opf::ExprArgs) << 32) | (unsigned long long) sizeof(opf::LaunchInfo))
+
     // ------------------------------------------------------------------------------------------- policies
     struct Exact {
         static constexpr bool fast = false;
@@ -125,6 +128,19 @@ namespace opf {
 #define OPF_WIN_MINBLOCKS 6
 #endif
 #define OPF_SHIFT(D, n) i + ((D) == 0 ? (n) : 0), j + ((D) == 1 ? (n) : 0), k + ((D) == 2 ? (n) : 0)
+
+    template <int N>
+    struct IC {
+        static constexpr int value = N;
+    };
+    // compile-time loop: fn(IC<LO>{}) ... fn(IC<HI>{})
+    template <int LO, int HI, class Fn>
+    __device__ __forceinline__ void static_for(Fn&& fn) {
+        if constexpr (LO <= HI) {
+            fn(IC<LO>{});
+            static_for<LO + 1, HI>(fn);
+        }
+    }
 
     // ------------------------------------------------------------------------------------------- tap sets
     // Compile-time footprint of an expression: for every field slot the set of relative offsets (di,dj,dk) it is read
@@ -253,6 +269,19 @@ namespace opf {
     OPF_BINOP(Ne, (x != y ? 1.0 : 0.0))
     OPF_BINOP(And, ((x != 0.0 && y != 0.0) ? 1.0 : 0.0))
     OPF_BINOP(Or, ((x != 0.0 || y != 0.0) ? 1.0 : 0.0))
+    // the remaining binary math functors of AMDS.hpp:40-51 (CUDA's double-precision libm; integer second operands are cast like the
+    // implicit conversion of the reference's call)
+    OPF_BINOP(FMod, fmod(x, y))
+    OPF_BINOP(Remainder, remainder(x, y))
+    OPF_BINOP(FDim, fdim(x, y))
+    OPF_BINOP(Hypot, hypot(x, y))
+    OPF_BINOP(ATan2, atan2(x, y))
+    OPF_BINOP(Ldexp, ldexp(x, (int) y))
+    OPF_BINOP(Scalbn, scalbn(x, (int) y))
+    OPF_BINOP(Scalbln, scalbn(x, (int) y))
+    OPF_BINOP(Nextafter, nextafter(x, y))
+    OPF_BINOP(Nexttoward, nextafter(x, y))
+    OPF_BINOP(Copysing, copysign(x, y))
 #undef OPF_BINOP
 
 #define OPF_UNIOP(Name, EXPR)                                                                                          \
@@ -288,6 +317,38 @@ namespace opf {
     OPF_UNIOP(Tan, tan(x))
     OPF_UNIOP(Tanh, tanh(x))
     OPF_UNIOP(Pow2, P::mul(x, x))
+    // the remaining unary math functors of AMDS.hpp:56-89 (integer-valued results are stored as Real, as an assignment to a
+    // CartesianField<Real> does in the reference)
+    OPF_UNIOP(Exp2, exp2(x))
+    OPF_UNIOP(Expm1, expm1(x))
+    OPF_UNIOP(Log10, log10(x))
+    OPF_UNIOP(Log2, log2(x))
+    OPF_UNIOP(Log1p, log1p(x))
+    OPF_UNIOP(Cbrt, cbrt(x))
+    OPF_UNIOP(ASin, asin(x))
+    OPF_UNIOP(ACos, acos(x))
+    OPF_UNIOP(ATan, atan(x))
+    OPF_UNIOP(Sinh, sinh(x))
+    OPF_UNIOP(Cosh, cosh(x))
+    OPF_UNIOP(ASinh, asinh(x))
+    OPF_UNIOP(ACosh, acosh(x))
+    OPF_UNIOP(ATanh, atanh(x))
+    OPF_UNIOP(Erf, erf(x))
+    OPF_UNIOP(Erfc, erfc(x))
+    OPF_UNIOP(TGamma, tgamma(x))
+    OPF_UNIOP(LGamma, lgamma(x))
+    OPF_UNIOP(Ceil, ceil(x))
+    OPF_UNIOP(Floor, floor(x))
+    OPF_UNIOP(Trunc, trunc(x))
+    OPF_UNIOP(Round, round(x))
+    OPF_UNIOP(LRound, (double) lround(x))
+    OPF_UNIOP(LLRound, (double) llround(x))
+    OPF_UNIOP(NearbyInt, nearbyint(x))
+    OPF_UNIOP(Rint, rint(x))
+    OPF_UNIOP(LRint, (double) lrint(x))
+    OPF_UNIOP(LLRint, (double) llrint(x))
+    OPF_UNIOP(ILogb, (double) ilogb(x))
+    OPF_UNIOP(Logb, logb(x))
 #undef OPF_UNIOP
 
     // CondOp::eval (Conditional.hpp:37-40)
@@ -340,10 +401,6 @@ namespace opf {
             constexpr int o = decltype(n)::value;                                                                      \
             return E::template ev<B + 1, P, A0, DI + (D == 0 ? o : 0), DJ + (D == 1 ? o : 0), DK + (D == 2 ? o : 0)>(c); \
         };
-    template <int N>
-    struct IC {
-        static constexpr int value = N;
-    };
     // mesh-coefficient accessors: O is the compile-time offset from the stencil's own index q along its axis
     enum { CF_X = 0, CF_DX = 1, CF_RDX = 2, CF_RDXH = 3, CF_RDXC = 4, CF_RDX2 = 5 };
     struct GAcc {// direct global loads (run-time coordinate evaluator)
@@ -585,6 +642,175 @@ namespace opf {
 #undef OPF_EVAL_BEGIN
 #undef OPF_EV_BEGIN
 
+    // ------------------------------------------------------------------------------------------- flux-limiter interpolators
+    // D1FluxLimiterImpl<Kernel, d, dir>::eval(u, e, i) (src/Core/Operator/Interpolator/D1FluxLimiter.hpp:41-190): the face value of e
+    // reconstructed from the upwind side, the side chosen per cell by the sign of the advecting field u:
+    //   u[i] > 0 ? Upwind(e, i) : Downwind(e, i)
+    // Cen2Cor (DIR 0) taps e at i-2 .. i+1 and yields a Corner value; Cor2Cen (DIR 1) taps i-1 .. i+2 and yields a Center value.
+    // "Linear" kernels (the kappa family, FluxLimiterKernels.hpp:32-52) combine the two slopes directly; the others limit through
+    // r = slope_f / (slope_u + 1e-16).  Operation order follows the reference so that Exact arithmetic is bit-identical.
+    template <int NUM, int DEN>
+    struct FlKappa {// KappaKernel<s>::eval(slop_u, slop_f): (1 + kappa) / 2. * slop_f + (1 - kappa) / 2. * slop_u
+        static constexpr bool linear = true;
+        template <class P>
+        __device__ __forceinline__ static double eval2(double su, double sf) {
+            constexpr double kappa = (double) NUM / (double) DEN;
+            return P::add(P::mul((1 + kappa) / 2., sf), P::mul((1 - kappa) / 2., su));
+        }
+    };
+    __device__ __forceinline__ double fl_max(double a, double b) { return a < b ? b : a; }// std::max
+    __device__ __forceinline__ double fl_min(double a, double b) { return b < a ? b : a; }// std::min
+    struct FlMinmodK {// std::max(0., std::min(r, 1.))
+        static constexpr bool linear = false;
+        template <class P>
+        __device__ __forceinline__ static double eval1(double r) { return fl_max(0., fl_min(r, 1.)); }
+    };
+    struct FlSuperbeeK {// std::max({0., std::min(2. * r, 1.), std::min(r, 2.)})
+        static constexpr bool linear = false;
+        template <class P>
+        __device__ __forceinline__ static double eval1(double r) { return fl_max(fl_max(0., fl_min(P::mul(2., r), 1.)), fl_min(r, 2.)); }
+    };
+    struct FlMusclK {// std::max(0., std::min({2 * r, (r + 1) / 2., 2.}))
+        static constexpr bool linear = false;
+        template <class P>
+        __device__ __forceinline__ static double eval1(double r) { return fl_max(0., fl_min(fl_min(P::mul(2., r), P::div(P::add(r, 1.), 2.)), 2.)); }
+    };
+    struct FlHarmonicK {// (r + std::fabs(r)) / (r + 1)
+        static constexpr bool linear = false;
+        template <class P>
+        __device__ __forceinline__ static double eval1(double r) { return P::div(P::add(r, fabs(r)), P::add(r, 1.)); }
+    };
+    struct FlAlbadaK {// r * (r + 1) / (r * r + 1)
+        static constexpr bool linear = false;
+        template <class P>
+        __device__ __forceinline__ static double eval1(double r) { return P::div(P::mul(r, P::add(r, 1.)), P::add(P::mul(r, r), 1.)); }
+    };
+    // one side: y2 +- dx * 0.5 * K(...) with slopes (y2 - y1) / (x2 - x1) and (y3 - y2) / (x3 - x2) assigned to upwind / far
+    template <class K, class P>
+    __device__ __forceinline__ double fl_side(double su, double sf, double y2, double h, bool plus) {
+        double t;
+        if constexpr (K::linear) t = P::mul(P::mul(h, 0.5), K::template eval2<P>(su, sf));
+        else {
+            const double r = P::div(sf, P::add(su, 1e-16));
+            t = P::mul(P::mul(P::mul(h, 0.5), K::template eval1<P>(r)), su);
+        }
+        return plus ? P::add(y2, t) : P::sub(y2, t);
+    }
+    // q0..q3: operand at (C2N) i-2, i-1, i, i+1 / (N2C) i-1, i, i+1, i+2
+    template <class K, int DIR, class P, class Acc>
+    __device__ __forceinline__ double fl_math(double uv, double q0, double q1, double q2, double q3, const Acc& m) {
+        if constexpr (DIR == 0) {
+            if (uv > 0.) {// D1FluxLimiterUpwindImpl<.., Cen2Cor> :46-63
+                const double x1 = P::add(m.template x<-2>(), P::mul(0.5, m.template dx<-2>()));
+                const double x2 = P::add(m.template x<-1>(), P::mul(0.5, m.template dx<-1>()));
+                const double x3 = P::add(m.template x<0>(), P::mul(0.5, m.template dx<0>()));
+                const double su = P::div(P::sub(q1, q0), P::sub(x2, x1)), sf = P::div(P::sub(q2, q1), P::sub(x3, x2));
+                return fl_side<K, P>(su, sf, q1, m.template dx<-1>(), true);
+            }
+            // D1FluxLimiterDownwindImpl<.., Cen2Cor> :95-112
+            const double x1 = P::add(m.template x<-1>(), P::mul(m.template dx<-1>(), 0.5));
+            const double x2 = P::add(m.template x<0>(), P::mul(m.template dx<0>(), 0.5));
+            const double x3 = P::add(m.template x<1>(), P::mul(m.template dx<1>(), 0.5));
+            const double su = P::div(P::sub(q3, q2), P::sub(x3, x2)), sf = P::div(P::sub(q2, q1), P::sub(x2, x1));
+            return fl_side<K, P>(su, sf, q2, m.template dx<0>(), false);
+        } else {
+            if (uv > 0.) {// D1FluxLimiterUpwindImpl<.., Cor2Cen> :67-84
+                const double x1 = m.template x<-1>(), x2 = m.template x<0>(), x3 = m.template x<1>();
+                const double su = P::div(P::sub(q1, q0), P::sub(x2, x1)), sf = P::div(P::sub(q2, q1), P::sub(x3, x2));
+                return fl_side<K, P>(su, sf, q1, m.template dx<0>(), true);
+            }
+            // D1FluxLimiterDownwindImpl<.., Cor2Cen> :116-133
+            const double x1 = m.template x<0>(), x2 = m.template x<1>(), x3 = m.template x<2>();
+            const double su = P::div(P::sub(q3, q2), P::sub(x3, x2)), sf = P::div(P::sub(q2, q1), P::sub(x2, x1));
+            return fl_side<K, P>(su, sf, q2, m.template dx<0>(), false);
+        }
+    }
+    template <class K, int DIR, int D, class U, class E>
+    struct FluxLim {
+        static constexpr int size = 1 + U::size + E::size;
+        static constexpr int maxaxis = (D > U::maxaxis ? D : U::maxaxis) > E::maxaxis ? (D > U::maxaxis ? D : U::maxaxis) : E::maxaxis;
+        static constexpr int nf = U::nf > E::nf ? U::nf : E::nf;
+        static constexpr int LO = DIR == 0 ? -2 : -1;
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            U::template taps<A0>(ts, in);
+            E::template taps<A0>(ts, tap_shift(in, D, LO, LO + 3));
+        }
+        template <int B, class P, bool A0>
+        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
+            const GAcc acc{a.ax[D], axis_of<D>(i, j, k)};
+            constexpr int BE = B + 1 + U::size;
+            const double uv = U::template eval<B + 1, P, A0>(a, i, j, k);
+            return fl_math<K, DIR, P>(uv, E::template eval<BE, P, A0>(a, OPF_SHIFT(D, LO)), E::template eval<BE, P, A0>(a, OPF_SHIFT(D, LO + 1)),
+                                      E::template eval<BE, P, A0>(a, OPF_SHIFT(D, LO + 2)), E::template eval<BE, P, A0>(a, OPF_SHIFT(D, LO + 3)), acc);
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            const WAcc<C, D, (D == 0 ? DI : (D == 1 ? DJ : DK))> acc{c};
+            constexpr int BE = B + 1 + U::size;
+            const double uv = U::template ev<B + 1, P, A0, DI, DJ, DK>(c);
+#define OPF_FL_TAP(o) E::template ev<BE, P, A0, DI + (D == 0 ? (o) : 0), DJ + (D == 1 ? (o) : 0), DK + (D == 2 ? (o) : 0)>(c)
+            return fl_math<K, DIR, P>(uv, OPF_FL_TAP(LO), OPF_FL_TAP(LO + 1), OPF_FL_TAP(LO + 2), OPF_FL_TAP(LO + 3), acc);
+#undef OPF_FL_TAP
+        }
+    };
+    // named nodes of the signature grammar: Fl<Scheme><C2N|N2C><axis, u, e>   (D1FluxLimiterBasedIntpOp.hpp:22-61)
+#define OPF_FLNODE(Name, ...)                                                                                          \
+    template <int D, class U, class E>                                                                                 \
+    struct Name##C2N : FluxLim<__VA_ARGS__, 0, D, U, E> {};                                                            \
+    template <int D, class U, class E>                                                                                 \
+    struct Name##N2C : FluxLim<__VA_ARGS__, 1, D, U, E> {};
+    OPF_FLNODE(FlCentral, FlKappa<1, 1>)
+    OPF_FLNODE(FlQuick, FlKappa<1, 2>)
+    OPF_FLNODE(FlCui, FlKappa<1, 3>)
+    OPF_FLNODE(FlFromm, FlKappa<0, 1>)
+    OPF_FLNODE(FlLui, FlKappa<-1, 1>)
+    OPF_FLNODE(FlMinmod, FlMinmodK)
+    OPF_FLNODE(FlSuperbee, FlSuperbeeK)
+    OPF_FLNODE(FlMuscl, FlMusclK)
+    OPF_FLNODE(FlHarmonic, FlHarmonicK)
+    OPF_FLNODE(FlAlbada, FlAlbadaK)
+#undef OPF_FLNODE
+
+    // Convolution<n0, n1[, n2]>::eval (src/Core/Operator/Convolution/Convolution.hpp:45-63): sum over the kernel box of
+    // kernel[idx - i + n/2] * e[idx], accumulated by rangeReduce_s in x-fastest order starting from 0.  The kernel tensor is a
+    // ScalarExpr operand: its entries travel in consecutive scalar slots S<K0>, S<K0+1>, ... (x-fastest like FixedSizeTensor).
+    template <int N0, int N1, int N2, int K0, class E>
+    struct Conv {
+        static constexpr int size = 1 + E::size, nf = E::nf;
+        static constexpr int maxaxis = (N2 > 1 ? 2 : (N1 > 1 ? 1 : 0)) > E::maxaxis ? (N2 > 1 ? 2 : (N1 > 1 ? 1 : 0)) : E::maxaxis;
+        static constexpr int H0 = N0 / 2, H1 = N1 / 2, H2 = N2 / 2;
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            E::template taps<A0>(ts, tap_shift(tap_shift(tap_shift(in, 0, -H0, H0), 1, -H1, H1), 2, -H2, H2));
+        }
+        template <int B, class P, bool A0>
+        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < N2; ++c)
+#pragma unroll
+                for (int b = 0; b < N1; ++b)
+#pragma unroll
+                    for (int x = 0; x < N0; ++x)
+                        acc = P::add(acc, P::mul(a.s[K0 + x + N0 * (b + N1 * c)], E::template eval<B + 1, P, A0>(a, i + x - H0, j + b - H1, k + c - H2)));
+            return acc;
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            double acc = 0.0;
+            static_for<0, N2 - 1>([&](auto cz) {
+                static_for<0, N1 - 1>([&](auto by) {
+                    static_for<0, N0 - 1>([&](auto ax) {
+                        constexpr int x = decltype(ax)::value, b = decltype(by)::value, z = decltype(cz)::value;
+                        acc = P::add(acc, P::mul(c.a.s[K0 + x + N0 * (b + N1 * z)], E::template ev<B + 1, P, A0, DI + x - H0, DJ + b - H1, DK + z - H2>(c)));
+                    });
+                });
+            });
+            return acc;
+        }
+    };
+
     // ------------------------------------------------------------------------------------------- skeletons
     // compound assignment (BasicArithOp, Constants.hpp:53; FieldAssigner.hpp:48-80).  `op` is warp-uniform.
     template <class P>
@@ -643,13 +869,6 @@ namespace opf {
     // (known at compile time from E::taps), each CX + halo wide.  Per march step only the leading row of every column is
     // loaded -- 128-bit vector loads for the aligned core -- and the window is rotated in registers, so a 7-point
     // stencil issues 3 vector loads + 2 scalar halo loads per CX cells instead of 7 scalar loads per cell.
-    template <int LO, int HI, class Fn>
-    __device__ __forceinline__ void static_for(Fn&& fn) {
-        if constexpr (LO <= HI) {
-            fn(IC<LO>{});
-            static_for<LO + 1, HI>(fn);
-        }
-    }
 
     template <class E, bool A0, int DIM>
     struct WinInfo {

@@ -64,6 +64,11 @@ class Expr:
             if isinstance(e, Scalar):
                 scalars.append(float(e.value))
                 return f"S<{len(scalars) - 1}>"
+            if e.name == "Conv":  # the kernel tensor's entries take consecutive scalar slots, x fastest (FixedSizeTensor order)
+                k0 = len(scalars)
+                scalars.extend(float(v) for v in e.kernel.reshape(-1, order="F"))
+                n = list(e.kernel.shape) + [1] * (3 - e.kernel.ndim)
+                return f"Conv<{n[0]},{n[1]},{n[2]},{k0},{rec(e.children[0])}>"
             parts = [rec(c) for c in e.children]
             if e.axis is not None:
                 parts.insert(0, str(e.axis))
@@ -121,6 +126,41 @@ def abs_(e): return Expr("Abs", (_wrap(e),))
 def pow2(e): return Expr("Pow2", (_wrap(e),))
 def max_(a, b): return Expr("Max", (_wrap(a), _wrap(b)))
 def min_(a, b): return Expr("Min", (_wrap(a), _wrap(b)))
+
+# the rest of the reference's point-wise family (src/Core/Operator/Arithmetic/AMDS.hpp:40-89)
+_UNARY_NODES = ['Exp2', 'Expm1', 'Log10', 'Log2', 'Log1p', 'Cbrt', 'ASin', 'ACos', 'ATan', 'Sinh', 'Cosh', 'ASinh', 'ACosh', 'ATanh', 'Erf', 'Erfc', 'TGamma', 'LGamma', 'Ceil', 'Floor', 'Trunc', 'Round', 'LRound', 'LLRound', 'NearbyInt', 'Rint', 'LRint', 'LLRint', 'ILogb', 'Logb', 'Exp', 'Log', 'Sin', 'Cos', 'Tan', 'Tanh', 'Not', 'Pos']
+_BINARY_NODES = ['FMod', 'Remainder', 'FDim', 'Hypot', 'ATan2', 'Ldexp', 'Scalbn', 'Scalbln', 'Nextafter', 'Nexttoward', 'Copysing', 'Pow']
+
+
+# flux-limiter interpolators (src/Core/Operator/Interpolator/D1FluxLimiterBasedIntpOp.hpp:22-61): d1IntpFl("Quick", axis, "C2N", u, e)
+FLUX_LIMITERS = ["Central", "Quick", "Cui", "Fromm", "Lui", "Minmod", "Superbee", "Muscl", "Harmonic", "Albada"]
+
+
+def d1IntpFl(scheme, axis, direction, u, e):
+    """D1Intp<D1QUICK | D1Minmod | ...><axis, Cen2Cor | Cor2Cen>(u, e): face value of e, upwinded by the sign of u"""
+    assert scheme in FLUX_LIMITERS and direction in ("C2N", "N2C")
+    return Expr(f"Fl{scheme}{direction}", (_wrap(u), _wrap(e)), axis=axis)
+
+
+def conv(e, kernel):
+    """conv(e, kernel) (src/Core/Operator/Convolution/Convolution.hpp): kernel = odd-sized array indexed [i0, i1(, i2)]"""
+    k = np.asarray(kernel, dtype=np.float64)
+    assert all(n % 2 == 1 for n in k.shape)
+    x = Expr("Conv", (_wrap(e),))
+    x.kernel = k
+    return x
+
+
+def unary(node, e):
+    """point-wise node by name, e.g. unary("Erf", u)"""
+    assert node in _UNARY_NODES + ["Sqrt", "Abs", "Pow2", "Neg"], node
+    return Expr(node, (_wrap(e),))
+
+
+def binary(node, a, b):
+    assert node in _BINARY_NODES + ["Min", "Max", "Add", "Sub", "Mul", "Div"], node
+    return Expr(node, (_wrap(a), _wrap(b)))
+
 
 
 # ----------------------------------------------------------------------------------------------- mesh

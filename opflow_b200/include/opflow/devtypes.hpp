@@ -38,6 +38,47 @@ namespace opf {
     template <class E> struct Tan;
     template <class E> struct Tanh;
     template <class E> struct Pow2;
+    template <class E> struct Exp2;
+    template <class E> struct Expm1;
+    template <class E> struct Log10;
+    template <class E> struct Log2;
+    template <class E> struct Log1p;
+    template <class E> struct Cbrt;
+    template <class E> struct ASin;
+    template <class E> struct ACos;
+    template <class E> struct ATan;
+    template <class E> struct Sinh;
+    template <class E> struct Cosh;
+    template <class E> struct ASinh;
+    template <class E> struct ACosh;
+    template <class E> struct ATanh;
+    template <class E> struct Erf;
+    template <class E> struct Erfc;
+    template <class E> struct TGamma;
+    template <class E> struct LGamma;
+    template <class E> struct Ceil;
+    template <class E> struct Floor;
+    template <class E> struct Trunc;
+    template <class E> struct Round;
+    template <class E> struct LRound;
+    template <class E> struct LLRound;
+    template <class E> struct NearbyInt;
+    template <class E> struct Rint;
+    template <class E> struct LRint;
+    template <class E> struct LLRint;
+    template <class E> struct ILogb;
+    template <class E> struct Logb;
+    template <class L, class R> struct FMod;
+    template <class L, class R> struct Remainder;
+    template <class L, class R> struct FDim;
+    template <class L, class R> struct Hypot;
+    template <class L, class R> struct ATan2;
+    template <class L, class R> struct Ldexp;
+    template <class L, class R> struct Scalbn;
+    template <class L, class R> struct Scalbln;
+    template <class L, class R> struct Nextafter;
+    template <class L, class R> struct Nexttoward;
+    template <class L, class R> struct Copysing;
     template <class C, class A, class B> struct Cond;
     template <int D, class E> struct D2C;
     template <int D, class E> struct D1C;

@@ -244,6 +244,47 @@ namespace OpFlow {
     OPF_FE_OP1(TanOp, Tan)
     OPF_FE_OP1(TanhOp, Tanh)
     OPF_FE_OP1(Pow2Op, Pow2)
+    OPF_FE_OP1(Exp2Op, Exp2)
+    OPF_FE_OP1(Expm1Op, Expm1)
+    OPF_FE_OP1(Log10Op, Log10)
+    OPF_FE_OP1(Log2Op, Log2)
+    OPF_FE_OP1(Log1pOp, Log1p)
+    OPF_FE_OP1(CbrtOp, Cbrt)
+    OPF_FE_OP1(ASinOp, ASin)
+    OPF_FE_OP1(ACosOp, ACos)
+    OPF_FE_OP1(ATanOp, ATan)
+    OPF_FE_OP1(SinhOp, Sinh)
+    OPF_FE_OP1(CoshOp, Cosh)
+    OPF_FE_OP1(ASinhOp, ASinh)
+    OPF_FE_OP1(ACoshOp, ACosh)
+    OPF_FE_OP1(ATanhOp, ATanh)
+    OPF_FE_OP1(ErfOp, Erf)
+    OPF_FE_OP1(ErfcOp, Erfc)
+    OPF_FE_OP1(TGammaOp, TGamma)
+    OPF_FE_OP1(LGammaOp, LGamma)
+    OPF_FE_OP1(CeilOp, Ceil)
+    OPF_FE_OP1(FloorOp, Floor)
+    OPF_FE_OP1(TruncOp, Trunc)
+    OPF_FE_OP1(RoundOp, Round)
+    OPF_FE_OP1(LRoundOp, LRound)
+    OPF_FE_OP1(LLRoundOp, LLRound)
+    OPF_FE_OP1(NearbyIntOp, NearbyInt)
+    OPF_FE_OP1(RintOp, Rint)
+    OPF_FE_OP1(LRintOp, LRint)
+    OPF_FE_OP1(LLRintOp, LLRint)
+    OPF_FE_OP1(ILogbOp, ILogb)
+    OPF_FE_OP1(LogbOp, Logb)
+    OPF_FE_OP2(FModOp, FMod)
+    OPF_FE_OP2(RemainderOp, Remainder)
+    OPF_FE_OP2(FDimOp, FDim)
+    OPF_FE_OP2(HypotOp, Hypot)
+    OPF_FE_OP2(ATan2Op, ATan2)
+    OPF_FE_OP2(LdexpOp, Ldexp)
+    OPF_FE_OP2(ScalbnOp, Scalbn)
+    OPF_FE_OP2(ScalblnOp, Scalbln)
+    OPF_FE_OP2(NextafterOp, Nextafter)
+    OPF_FE_OP2(NexttowardOp, Nexttoward)
+    OPF_FE_OP2(CopysingOp, Copysing)
 #undef OPF_FE_OP1
 #undef OPF_FE_OP2
     struct CondOp {
@@ -296,7 +337,54 @@ namespace OpFlow {
     OPF_FE_FUNC1(tan, TanOp)
     OPF_FE_FUNC1(tanh, TanhOp)
     OPF_FE_FUNC1(pow2, Pow2Op)
+    OPF_FE_FUNC1(exp2, Exp2Op)
+    OPF_FE_FUNC1(expm1, Expm1Op)
+    OPF_FE_FUNC1(log10, Log10Op)
+    OPF_FE_FUNC1(log2, Log2Op)
+    OPF_FE_FUNC1(log1p, Log1pOp)
+    OPF_FE_FUNC1(cbrt, CbrtOp)
+    OPF_FE_FUNC1(asin, ASinOp)
+    OPF_FE_FUNC1(acos, ACosOp)
+    OPF_FE_FUNC1(atan, ATanOp)
+    OPF_FE_FUNC1(sinh, SinhOp)
+    OPF_FE_FUNC1(cosh, CoshOp)
+    OPF_FE_FUNC1(asinh, ASinhOp)
+    OPF_FE_FUNC1(acosh, ACoshOp)
+    OPF_FE_FUNC1(atanh, ATanhOp)
+    OPF_FE_FUNC1(erf, ErfOp)
+    OPF_FE_FUNC1(erfc, ErfcOp)
+    OPF_FE_FUNC1(tgamma, TGammaOp)
+    OPF_FE_FUNC1(lgamma, LGammaOp)
+    OPF_FE_FUNC1(ceil, CeilOp)
+    OPF_FE_FUNC1(floor, FloorOp)
+    OPF_FE_FUNC1(trunc, TruncOp)
+    OPF_FE_FUNC1(round, RoundOp)
+    OPF_FE_FUNC1(lround, LRoundOp)
+    OPF_FE_FUNC1(llround, LLRoundOp)
+    OPF_FE_FUNC1(nearbyint, NearbyIntOp)
+    OPF_FE_FUNC1(rint, RintOp)
+    OPF_FE_FUNC1(lrint, LRintOp)
+    OPF_FE_FUNC1(llrint, LLRintOp)
+    OPF_FE_FUNC1(ilogb, ILogbOp)
+    OPF_FE_FUNC1(logb, LogbOp)
 #undef OPF_FE_FUNC1
+#define OPF_FE_FUNC2(fname, OpName)                                                                                    \
+    template <typename A, typename B>                                                                                  \
+    requires internal::ExprOperands<A, B> auto fname(A&& a, B&& b) {                                                   \
+        return makeExpression<OpName>(std::forward<A>(a), std::forward<B>(b));                                         \
+    }
+    OPF_FE_FUNC2(fmod, FModOp)
+    OPF_FE_FUNC2(remainder, RemainderOp)
+    OPF_FE_FUNC2(fdim, FDimOp)
+    OPF_FE_FUNC2(hypot, HypotOp)
+    OPF_FE_FUNC2(atan2, ATan2Op)
+    OPF_FE_FUNC2(ldexp, LdexpOp)
+    OPF_FE_FUNC2(scalbn, ScalbnOp)
+    OPF_FE_FUNC2(scalbln, ScalblnOp)
+    OPF_FE_FUNC2(nextafter, NextafterOp)
+    OPF_FE_FUNC2(nexttoward, NexttowardOp)
+    OPF_FE_FUNC2(copysign, CopysingOp)
+#undef OPF_FE_FUNC2
     template <typename A, typename B>
     requires internal::ExprOperands<A, B> auto min(A&& a, B&& b) {
         return makeExpression<MinOp>(std::forward<A>(a), std::forward<B>(b));
@@ -394,7 +482,7 @@ namespace OpFlow {
             using DevT = typename E::template Dev<0, 0>::type;
             static const bool once = [&] {// the library's own instantiation (all dimensions) wins if it exists
                 if (!opf_expr_is_registered(fl.sig.c_str()))
-                    check_rc(opf_expr_register(fl.sig.c_str(), &opf::launcher<DevT, 1 << (DIM - 1)>), "opf_expr_register");
+                    check_rc(opf_expr_register_abi(fl.sig.c_str(), &opf::launcher<DevT, 1 << (DIM - 1)>, OPF_DEVICE_ABI), "opf_expr_register");
                 return true;
             }();
             (void) once;

@@ -159,6 +159,11 @@ namespace OpFlow {
             p.precond_max_iter = 1;
             p.num_pre_relax = p.num_post_relax = 1;
             p.relax_type = 1;
+            if constexpr (requires { solver.params.kDim; }) {
+                if (solver.params.kDim) p.k_dim = *solver.params.kDim;
+                if constexpr (requires { solver.params.augDim; })
+                    if (solver.params.augDim) p.k_dim = (p.k_dim > 0 ? p.k_dim : 5) + *solver.params.augDim;
+            }
             if constexpr (S::precType != StructSolverType::None) internal::fill_precond_params(p, solver.precParams);
             else
                 internal::fill_precond_params(p, solver.params);
@@ -179,7 +184,7 @@ namespace OpFlow {
                     sh.fields.push_back(nullptr);
                     lhs.flatten(sh);
                     const std::string rs = "Sub<F<0>," + sh.sig + ">";
-                    if (!opf_expr_is_registered(rs.c_str())) internal::check_rc(opf_expr_register(rs.c_str(), &opf::launcher<ResT, 1 << (T::dim - 1)>), "opf_expr_register");
+                    if (!opf_expr_is_registered(rs.c_str())) internal::check_rc(opf_expr_register_abi(rs.c_str(), &opf::launcher<ResT, 1 << (T::dim - 1)>, OPF_DEVICE_ABI), "opf_expr_register");
                     return true;
                 }();
                 (void) once;

@@ -312,8 +312,9 @@ void orc_update_padding(orc_field* f, const orc_mesh* m) {
 /* ---------------------------------------------------------------------------------------------- expression interpreter
  * The signature grammar is the one of include/opflow_b200.h; evaluation follows each Op::eval of the reference. */
 typedef struct {
-    char name[12];
+    char name[20];
     int axis, leaf, nchild, child[3];
+    int conv[4]; /* Conv<n0,n1,n2,k0,E> */
     int scalar, loc[3];
     orc_range acc, local, logical;
 } onode;
@@ -337,7 +338,7 @@ static int parse_node(otree* t) {
     b = t->pos;
     while (isalnum((unsigned char) t->s[t->pos])) t->pos++;
     l = t->pos - b;
-    if (l <= 0 || l > 11 || t->s[t->pos] != '<') {
+    if (l <= 0 || l > 19 || t->s[t->pos] != '<') {
         t->err = 1;
         return -1;
     }
@@ -353,7 +354,15 @@ static int parse_node(otree* t) {
             if (n->leaf + 1 > t->nscalars) t->nscalars = n->leaf + 1;
         }
     } else {
-        if (isdigit((unsigned char) t->s[t->pos])) {
+        if (!strcmp(n->name, "Conv")) {
+            int q;
+            for (q = 0; q < 4; ++q) {
+                n->conv[q] = (int) strtol(t->s + t->pos, NULL, 10);
+                while (isdigit((unsigned char) t->s[t->pos])) t->pos++;
+                t->pos++; /* ',' */
+            }
+            if (n->conv[3] + n->conv[0] * n->conv[1] * n->conv[2] > t->nscalars) t->nscalars = n->conv[3] + n->conv[0] * n->conv[1] * n->conv[2];
+        } else if (isdigit((unsigned char) t->s[t->pos])) {
             n->axis = t->s[t->pos] - '0';
             t->pos += 2; /* digit and ',' */
         }
@@ -431,6 +440,29 @@ static int prepare(otree* t, int id, orc_field** fields) {
         inherit(n, &t->n[n->child[0]]);
         n->loc[d] = LOC_CENTER;
         n->acc.end[d]--, n->logical.end[d]--, n->local.end[d]--;
+    } else if (!strncmp(n->name, "Fl", 2) && strstr(n->name, "C2N")) {/* D1FluxLimiter.hpp:155-171: props from arg2 */
+        if (t->n[n->child[1]].loc[d] != LOC_CENTER) return 2;
+        inherit(n, &t->n[n->child[1]]);
+        n->loc[d] = LOC_CORNER;
+        n->acc.start[d] += 2, n->acc.end[d] -= 1;
+        n->local.start[d] += 2, n->local.end[d] -= 1;
+        n->logical.start[d] += 2, n->logical.end[d] -= 1;
+    } else if (!strncmp(n->name, "Fl", 2) && strstr(n->name, "N2C")) {/* D1FluxLimiter.hpp:188-203 */
+        if (t->n[n->child[1]].loc[d] != LOC_CORNER) return 2;
+        inherit(n, &t->n[n->child[1]]);
+        n->loc[d] = LOC_CENTER;
+        n->acc.start[d] += 1, n->acc.end[d] -= 2;
+        n->local.start[d] += 1, n->local.end[d] -= 2;
+        n->logical.start[d] += 1, n->logical.end[d] -= 2;
+    } else if (is(n, "Conv")) {/* Convolution.hpp:66-82 */
+        int a;
+        inherit(n, &t->n[n->child[0]]);
+        for (a = 0; a < 3; ++a) {
+            const int h = n->conv[a] / 2;
+            n->acc.start[a] += h, n->acc.end[a] -= h;
+            n->local.start[a] += h, n->local.end[a] -= h;
+            n->logical.start[a] += h, n->logical.end[a] -= h;
+        }
     } else if (is(n, "Cond")) {/* Conditional.hpp:45-70 */
         onode *a = &t->n[n->child[0]], *b = &t->n[n->child[1]], *cc = &t->n[n->child[2]];
         inherit(n, b);
@@ -479,12 +511,94 @@ static double weno_core(double d1, double d2, double d3, double d4, double d5) {
     return w1 * ddx1 + w2 * ddx2 + w3 * ddx3;
 }
 
+static double mind(double a, double b) { return b < a ? b : a; } /* std::min */
+
+/* FluxLimiterKernels.hpp:32-80; kind = the scheme part of the node name */
+static int fl_linear(const char* k) { return !strncmp(k, "Central", 7) || !strncmp(k, "Quick", 5) || !strncmp(k, "Cui", 3) || !strncmp(k, "Fromm", 5) || !strncmp(k, "Lui", 3); }
+static double fl_kappa(const char* k, double su, double sf) {/* KappaKernel::eval(slop_u, slop_f) :35-51 */
+    double kappa;
+    if (!strncmp(k, "Central", 7)) kappa = 1;
+    else if (!strncmp(k, "Quick", 5))
+        kappa = 0.5;
+    else if (!strncmp(k, "Cui", 3))
+        kappa = 1. / 3.;
+    else if (!strncmp(k, "Fromm", 5))
+        kappa = 0.;
+    else
+        kappa = -1.;
+    return (1 + kappa) / 2. * sf + (1 - kappa) / 2. * su;
+}
+static double fl_r(const char* k, double r) {
+    if (!strncmp(k, "Minmod", 6)) return maxd(0., mind(r, 1.));                                    /* :56 */
+    if (!strncmp(k, "Superbee", 8)) return maxd(maxd(0., mind(2. * r, 1.)), mind(r, 2.));          /* :61, initializer-list max = left fold */
+    if (!strncmp(k, "Muscl", 5)) return maxd(0., mind(mind(2 * r, (r + 1) / 2.), 2.));             /* :66 */
+    if (!strncmp(k, "Harmonic", 8)) return (r + fabs(r)) / (r + 1);                                /* :71 */
+    return r * (r + 1) / (r * r + 1);                                                              /* vanAlbada :76 */
+}
+static double fl_side(const char* k, double su, double sf, double y2, double h, int plus) {
+    double t;
+    if (fl_linear(k)) t = h * 0.5 * fl_kappa(k, su, sf);
+    else {
+        double r = sf / (su + 1e-16);
+        t = h * 0.5 * fl_r(k, r) * su;
+    }
+    return plus ? y2 + t : y2 - t;
+}
+
 static double eval(const ectx* c, int id, const int* g) {
     const onode* n = &c->t->n[id];
     const int d = n->axis;
     int gm[3] = {g[0], g[1], g[2]}, gp[3] = {g[0], g[1], g[2]};
     if (is(n, "F")) return f_get(c->fields[n->leaf], g);
     if (is(n, "S")) return c->scalars[n->leaf];
+    if (!strncmp(n->name, "Fl", 2)) {/* D1FluxLimiterImpl::eval (D1FluxLimiter.hpp:148-151,182-185) */
+        const char* k = n->name + 2;
+        const orc_mesh* m = c->m;
+        const int q = g[d], e = n->child[1], c2n = strstr(n->name, "C2N") != NULL;
+        const double uv = eval(c, n->child[0], g);
+        double y[5];
+        int o, gg[3] = {g[0], g[1], g[2]};
+        for (o = -2; o <= 2; ++o) {
+            if ((c2n && o == 2) || (!c2n && o == -2)) {
+                y[o + 2] = 0.0;
+                continue;
+            }
+            gg[d] = q + o;
+            y[o + 2] = eval(c, e, gg);
+        }
+#define Y(o) y[(o) + 2]
+        if (c2n) {
+            if (uv > 0.) {/* :46-63 */
+                double x1 = mesh_x(m, d, q - 2) + 0.5 * mesh_dx(m, d, q - 2), x2 = mesh_x(m, d, q - 1) + 0.5 * mesh_dx(m, d, q - 1),
+                       x3 = mesh_x(m, d, q) + 0.5 * mesh_dx(m, d, q);
+                return fl_side(k, (Y(-1) - Y(-2)) / (x2 - x1), (Y(0) - Y(-1)) / (x3 - x2), Y(-1), mesh_dx(m, d, q - 1), 1);
+            } else {/* :95-112 */
+                double x1 = mesh_x(m, d, q - 1) + mesh_dx(m, d, q - 1) * 0.5, x2 = mesh_x(m, d, q) + mesh_dx(m, d, q) * 0.5,
+                       x3 = mesh_x(m, d, q + 1) + mesh_dx(m, d, q + 1) * 0.5;
+                return fl_side(k, (Y(1) - Y(0)) / (x3 - x2), (Y(0) - Y(-1)) / (x2 - x1), Y(0), mesh_dx(m, d, q), 0);
+            }
+        } else {
+            if (uv > 0.) {/* :67-84 */
+                double x1 = mesh_x(m, d, q - 1), x2 = mesh_x(m, d, q), x3 = mesh_x(m, d, q + 1);
+                return fl_side(k, (Y(0) - Y(-1)) / (x2 - x1), (Y(1) - Y(0)) / (x3 - x2), Y(0), mesh_dx(m, d, q), 1);
+            } else {/* :116-133 */
+                double x1 = mesh_x(m, d, q), x2 = mesh_x(m, d, q + 1), x3 = mesh_x(m, d, q + 2);
+                return fl_side(k, (Y(2) - Y(1)) / (x3 - x2), (Y(1) - Y(0)) / (x2 - x1), Y(1), mesh_dx(m, d, q), 0);
+            }
+        }
+#undef Y
+    }
+    if (is(n, "Conv")) {/* Convolution::eval (Convolution.hpp:45-63): rangeReduce_s, x fastest, identity 0 */
+        double acc = 0.0;
+        int a, b, z, gg[3];
+        for (z = 0; z < n->conv[2]; ++z)
+            for (b = 0; b < n->conv[1]; ++b)
+                for (a = 0; a < n->conv[0]; ++a) {
+                    gg[0] = g[0] + a - n->conv[0] / 2, gg[1] = g[1] + b - n->conv[1] / 2, gg[2] = g[2] + z - n->conv[2] / 2;
+                    acc = acc + c->scalars[n->conv[3] + a + n->conv[0] * (b + n->conv[1] * z)] * eval(c, n->child[0], gg);
+                }
+        return acc;
+    }
     if (d >= 0) {
         const int ch = n->child[0], center = c->t->n[ch].loc[d] == LOC_CENTER, q = g[d];
         const orc_mesh* m = c->m;
@@ -538,6 +652,37 @@ static double eval(const ectx* c, int id, const int* g) {
         if (is(n, "Tan")) return tan(x);
         if (is(n, "Tanh")) return tanh(x);
         if (is(n, "Pow2")) return x * x;
+        /* AMDS.hpp:56-89: libm, integer-valued results stored as Real */
+        if (is(n, "Exp2")) return exp2(x);
+        if (is(n, "Expm1")) return expm1(x);
+        if (is(n, "Log10")) return log10(x);
+        if (is(n, "Log2")) return log2(x);
+        if (is(n, "Log1p")) return log1p(x);
+        if (is(n, "Cbrt")) return cbrt(x);
+        if (is(n, "ASin")) return asin(x);
+        if (is(n, "ACos")) return acos(x);
+        if (is(n, "ATan")) return atan(x);
+        if (is(n, "Sinh")) return sinh(x);
+        if (is(n, "Cosh")) return cosh(x);
+        if (is(n, "ASinh")) return asinh(x);
+        if (is(n, "ACosh")) return acosh(x);
+        if (is(n, "ATanh")) return atanh(x);
+        if (is(n, "Erf")) return erf(x);
+        if (is(n, "Erfc")) return erfc(x);
+        if (is(n, "TGamma")) return tgamma(x);
+        if (is(n, "LGamma")) return lgamma(x);
+        if (is(n, "Ceil")) return ceil(x);
+        if (is(n, "Floor")) return floor(x);
+        if (is(n, "Trunc")) return trunc(x);
+        if (is(n, "Round")) return round(x);
+        if (is(n, "LRound")) return (double) lround(x);
+        if (is(n, "LLRound")) return (double) llround(x);
+        if (is(n, "NearbyInt")) return nearbyint(x);
+        if (is(n, "Rint")) return rint(x);
+        if (is(n, "LRint")) return (double) lrint(x);
+        if (is(n, "LLRint")) return (double) llrint(x);
+        if (is(n, "ILogb")) return (double) ilogb(x);
+        if (is(n, "Logb")) return logb(x);
     } else {
         double x = eval(c, n->child[0], g), y = eval(c, n->child[1], g);
         if (is(n, "Add")) return x + y;
@@ -547,6 +692,18 @@ static double eval(const ectx* c, int id, const int* g) {
         if (is(n, "Min")) return y < x ? y : x;
         if (is(n, "Max")) return x < y ? y : x;
         if (is(n, "Pow")) return pow(x, y);
+        /* AMDS.hpp:40-51 */
+        if (is(n, "FMod")) return fmod(x, y);
+        if (is(n, "Remainder")) return remainder(x, y);
+        if (is(n, "FDim")) return fdim(x, y);
+        if (is(n, "Hypot")) return hypot(x, y);
+        if (is(n, "ATan2")) return atan2(x, y);
+        if (is(n, "Ldexp")) return ldexp(x, (int) y);
+        if (is(n, "Scalbn")) return scalbn(x, (int) y);
+        if (is(n, "Scalbln")) return scalbn(x, (int) y);
+        if (is(n, "Nextafter")) return nextafter(x, y);
+        if (is(n, "Nexttoward")) return nextafter(x, y);
+        if (is(n, "Copysing")) return copysign(x, y);
         if (is(n, "Lt")) return x < y;
         if (is(n, "Le")) return x <= y;
         if (is(n, "Gt")) return x > y;
