@@ -88,5 +88,26 @@ namespace opf {
     template <int D, class E> struct WenoUp;
     template <int D, class E> struct IntpC2N;
     template <int D, class E> struct IntpN2C;
+    template <int D, class U, class E> struct FlCentralC2N;
+    template <int D, class U, class E> struct FlCentralN2C;
+    template <int D, class U, class E> struct FlQuickC2N;
+    template <int D, class U, class E> struct FlQuickN2C;
+    template <int D, class U, class E> struct FlCuiC2N;
+    template <int D, class U, class E> struct FlCuiN2C;
+    template <int D, class U, class E> struct FlFrommC2N;
+    template <int D, class U, class E> struct FlFrommN2C;
+    template <int D, class U, class E> struct FlLuiC2N;
+    template <int D, class U, class E> struct FlLuiN2C;
+    template <int D, class U, class E> struct FlMinmodC2N;
+    template <int D, class U, class E> struct FlMinmodN2C;
+    template <int D, class U, class E> struct FlSuperbeeC2N;
+    template <int D, class U, class E> struct FlSuperbeeN2C;
+    template <int D, class U, class E> struct FlMusclC2N;
+    template <int D, class U, class E> struct FlMusclN2C;
+    template <int D, class U, class E> struct FlHarmonicC2N;
+    template <int D, class U, class E> struct FlHarmonicN2C;
+    template <int D, class U, class E> struct FlAlbadaC2N;
+    template <int D, class U, class E> struct FlAlbadaN2C;
+    template <int N0, int N1, int N2, int K0, class E> struct Conv;
 }// namespace opf
 #endif

@@ -453,17 +453,166 @@ namespace OpFlow {
     OPF_FE_THREED(dx, dy, dz, d1)
     OPF_FE_THREED(d2x, d2y, d2z, d2)
 #undef OPF_FE_THREED
-    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
-    auto d1IntpCenterToCorner(E&& expr) {
-        return makeExpression<Kernel<dim, IntpDirection::Cen2Cor>>(std::forward<E>(expr));
+    // IntpInterface.hpp:28-44: the operands are forwarded as they come -- (e) for D1Linear, (u, e) for the flux-limiter kernels
+    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename... E>
+    auto d1IntpCenterToCorner(E&&... expr) {
+        return makeExpression<Kernel<dim, IntpDirection::Cen2Cor>>(std::forward<E>(expr)...);
     }
-    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
-    auto d1IntpCornerToCenter(E&& expr) {
-        return makeExpression<Kernel<dim, IntpDirection::Cor2Cen>>(std::forward<E>(expr));
+    template <std::size_t dim, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename... E>
+    auto d1IntpCornerToCenter(E&&... expr) {
+        return makeExpression<Kernel<dim, IntpDirection::Cor2Cen>>(std::forward<E>(expr)...);
     }
-    template <std::size_t dim, IntpDirection dir, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename E>
-    auto d1Intp(E&& expr) {
-        return makeExpression<Kernel<dim, dir>>(std::forward<E>(expr));
+    template <std::size_t dim, IntpDirection dir, template <std::size_t, IntpDirection> typename Kernel = D1Linear, typename... E>
+    auto d1Intp(E&&... expr) {
+        return makeExpression<Kernel<dim, dir>>(std::forward<E>(expr)...);
+    }
+
+    // ------------------------------------------------------------------------------------------------ flux-limiter interpolators
+    // FluxLimiterKernels.hpp:22-80 + D1FluxLimiter.hpp + D1FluxLimiterBasedIntpOp.hpp:22-61.  The kernel TYPES only select the device
+    // node (opf::Fl<Scheme>C2N / N2C, opf_device.cuh); the generalised piecewise-linear families (SPL / GPL) have no device node yet.
+    enum class KappaScheme { CDS, QUICK, CUI, Fromm, LUI };
+    template <KappaScheme s>
+    struct KappaKernel {};
+    struct MinmodKernel {};
+    struct SuperbeeKernel {};
+    struct MUSCLKernel {};
+    struct HarmonicKernel {};
+    struct vanAlbadaKernel {};
+    namespace internal {
+        template <typename K>
+        struct FlNode;
+#define OPF_FE_FLNODE(KernelType, Node)                                                                                \
+    template <>                                                                                                        \
+    struct FlNode<KernelType> {                                                                                        \
+        static constexpr const char *c2n = #Node "C2N", *n2c = #Node "N2C";                                            \
+        template <int D, class U, class E>                                                                             \
+        using C2N = opf::Node##C2N<D, U, E>;                                                                           \
+        template <int D, class U, class E>                                                                             \
+        using N2C = opf::Node##N2C<D, U, E>;                                                                           \
+    };
+        OPF_FE_FLNODE(KappaKernel<KappaScheme::CDS>, FlCentral)
+        OPF_FE_FLNODE(KappaKernel<KappaScheme::QUICK>, FlQuick)
+        OPF_FE_FLNODE(KappaKernel<KappaScheme::CUI>, FlCui)
+        OPF_FE_FLNODE(KappaKernel<KappaScheme::Fromm>, FlFromm)
+        OPF_FE_FLNODE(KappaKernel<KappaScheme::LUI>, FlLui)
+        OPF_FE_FLNODE(MinmodKernel, FlMinmod)
+        OPF_FE_FLNODE(SuperbeeKernel, FlSuperbee)
+        OPF_FE_FLNODE(MUSCLKernel, FlMuscl)
+        OPF_FE_FLNODE(HarmonicKernel, FlHarmonic)
+        OPF_FE_FLNODE(vanAlbadaKernel, FlAlbada)
+#undef OPF_FE_FLNODE
+        template <typename K, std::size_t d, IntpDirection dir>
+        struct D1FluxLimiterImpl {// D1FluxLimiter.hpp:137-203: operands (u, e)
+            static constexpr const char* name = dir == IntpDirection::Cen2Cor ? FlNode<K>::c2n : FlNode<K>::n2c;
+            static constexpr int axis = static_cast<int>(d);
+            static constexpr int bc_width = 2;
+            template <class U, class E>
+            using dev = std::conditional_t<dir == IntpDirection::Cen2Cor, typename FlNode<K>::template C2N<static_cast<int>(d), U, E>,
+                                           typename FlNode<K>::template N2C<static_cast<int>(d), U, E>>;
+        };
+    }// namespace internal
+    template <typename Kernel>
+    struct D1FluxLimiterGen {
+        template <std::size_t d, IntpDirection dir>
+        using Op = internal::D1FluxLimiterImpl<Kernel, d, dir>;
+    };
+    template <std::size_t d, IntpDirection dir>
+    using D1QUICK = typename D1FluxLimiterGen<KappaKernel<KappaScheme::QUICK>>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Central = typename D1FluxLimiterGen<KappaKernel<KappaScheme::CDS>>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1CUI = typename D1FluxLimiterGen<KappaKernel<KappaScheme::CUI>>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Fromm = typename D1FluxLimiterGen<KappaKernel<KappaScheme::Fromm>>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1LinearUpwind = typename D1FluxLimiterGen<KappaKernel<KappaScheme::LUI>>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Minmod = typename D1FluxLimiterGen<MinmodKernel>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Superbee = typename D1FluxLimiterGen<SuperbeeKernel>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1MUSCL = typename D1FluxLimiterGen<MUSCLKernel>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Harmonic = typename D1FluxLimiterGen<HarmonicKernel>::template Op<d, dir>;
+    template <std::size_t d, IntpDirection dir>
+    using D1Albada = typename D1FluxLimiterGen<vanAlbadaKernel>::template Op<d, dir>;
+
+    // ------------------------------------------------------------------------------------------------ convolution
+    // conv(expr, kernel) (Convolution.hpp:160-170): the kernel tensor's entries travel as consecutive scalar leaves (x fastest)
+    namespace DS {
+        template <typename T, int... ns>
+        struct FixedSizeTensor {// DataStructures/Arrays/Tensor/FixedSizeTensor.hpp: dense, first index fastest
+            static constexpr int dim = sizeof...(ns);
+            static constexpr std::array<int, sizeof...(ns)> dims {ns...};
+            static constexpr int total = (ns * ...);
+            std::array<T, total> val {};
+            constexpr FixedSizeTensor() = default;
+            template <typename... V>
+            requires(sizeof...(V) >= 1 && (std::is_convertible_v<V, T> && ...)) constexpr FixedSizeTensor(V... v) {
+                if constexpr (sizeof...(V) == 1) val.fill((static_cast<T>(v), ...));
+                else
+                    val = {static_cast<T>(v)...};
+            }
+            constexpr int offset(const auto& idx) const {
+                int o = 0, s = 1;
+                for (int d = 0; d < dim; ++d) {
+                    o += idx[d] * s;
+                    s *= dims[d];
+                }
+                return o;
+            }
+            constexpr T& operator[](const MDIndex<dim>& idx) { return val[offset(idx)]; }
+            constexpr const T& operator[](const MDIndex<dim>& idx) const { return val[offset(idx)]; }
+        };
+    }// namespace DS
+    template <typename E, int N0, int N1, int N2>
+    struct ConvExpr : ExprTag {
+        E arg;
+        std::array<Real, N0 * N1 * N2> ker;
+        static constexpr bool has_unknown = E::has_unknown;
+        static constexpr int dim = E::dim;
+        mutable DS::Range<(dim > 0 ? dim : 1)> accessibleRange, localRange, logicalRange, assignableRange;
+        mutable std::array<LocOnMesh, (dim > 0 ? dim : 1)> loc {};
+        template <int NF, int NS>
+        struct Dev {
+            using D0 = typename E::template Dev<NF, NS + N0 * N1 * N2>;
+            using type = opf::Conv<N0, N1, N2, NS, typename D0::type>;
+            static constexpr int nf = D0::nf, ns = D0::ns;
+        };
+        void flatten(internal::Flat& fl) const {
+            fl.sig += "Conv<" + std::to_string(N0) + "," + std::to_string(N1) + "," + std::to_string(N2) + "," + std::to_string(fl.scalars.size()) + ",";
+            for (Real v : ker) fl.scalars.push_back(v);
+            arg.flatten(fl);
+            fl.sig += ">";
+        }
+        void prepare() const {
+            internal::Flat fl;
+            flatten(fl);
+            opf_range r;
+            int l[OPF_MAX_DIM];
+            internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 2, &r, l), "opf_expr_prepare");
+            accessibleRange = internal::from_c<dim>(r);
+            internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 0, &r, nullptr), "opf_expr_prepare");
+            localRange = internal::from_c<dim>(r);
+            internal::check_rc(opf_expr_prepare(fl.sig.c_str(), fl.fields.data(), (int) fl.fields.size(), 3, &r, nullptr), "opf_expr_prepare");
+            logicalRange = internal::from_c<dim>(r);
+            assignableRange.setEmpty();
+            for (int d = 0; d < dim; ++d) loc[d] = static_cast<LocOnMesh>(l[d]);
+        }
+    };
+    template <typename E, typename D, int... ns>
+    requires ExprType<E> auto conv(E&& expr, const DS::FixedSizeTensor<D, ns...>& kernel) {
+        constexpr std::array<int, 3> n = [] {
+            std::array<int, 3> a {1, 1, 1};
+            int k = 0;
+            ((a[k++] = ns), ...);
+            return a;
+        }();
+        static_assert(sizeof...(ns) <= 3 && ((ns % 2 == 1) && ...), "conv(): odd kernel extents, at most three axes");
+        using W = internal::wrapped_t<E>;
+        ConvExpr<W, n[0], n[1], n[2]> c {{}, internal::wrap(std::forward<E>(expr)), {}};
+        for (int i = 0; i < kernel.total; ++i) c.ker[i] = static_cast<Real>(kernel.val[i]);
+        return c;
     }
 
     // ------------------------------------------------------------------------------------------------ kernel registration

@@ -12,10 +12,20 @@ using Field = CartesianField<Real, Mesh>;
 
 static std::ostringstream out;
 static bool first = true;
+static const Mesh* g_mesh = nullptr;
 
 template <typename T>
 static void emit(const char* name, int axis, const char* dir, T&& t) {
     t.prepare();
+#ifdef OPFLOW_B200
+    // the B200 front-end evaluates expressions on the device: assign into a field of the result's location, read that back
+    auto dst = ExprBuilder<Field>().setMesh(*g_mesh).setLoc({t.loc[0], t.loc[1]}).setExt(2).build();
+    dst = 0.;
+    dst = t;
+    auto value = [&](auto&& i) { return (double) dst.evalAt(i); };
+#else
+    auto value = [&](auto&& i) { return (double) t.evalAt(i); };
+#endif
     out << (first ? "" : ",\n") << "{\"node\":\"" << name << "\",\"axis\":" << axis << ",\"dir\":\"" << dir << "\",\"acc\":[[" << t.accessibleRange.start[0] << ","
         << t.accessibleRange.start[1] << "],[" << t.accessibleRange.end[0] << "," << t.accessibleRange.end[1] << "]],\"local\":[[" << t.localRange.start[0] << ","
         << t.localRange.start[1] << "],[" << t.localRange.end[0] << "," << t.localRange.end[1] << "]],\"logical\":[[" << t.logicalRange.start[0] << ","
@@ -25,7 +35,7 @@ static void emit(const char* name, int axis, const char* dir, T&& t) {
     bool f2 = true;
     rangeFor_s(t.accessibleRange, [&](auto&& i) {
         char buf[40];
-        snprintf(buf, sizeof buf, "\"%a\"", (double) t.evalAt(i));
+        snprintf(buf, sizeof buf, "\"%a\"", value(i));
         out << (f2 ? "" : ",") << buf;
         f2 = false;
     });
@@ -41,6 +51,7 @@ int main() {
     auto sx = [&](int i) { double s = (double) i / (nx - 1); return 2.0 * (s + 0.15 * std::sin(2 * PI * s) / (2 * PI)); };
     auto sy = [&](int i) { double s = (double) i / (ny - 1); return 1.0 * (s + 0.15 * std::sin(2 * PI * s) / (2 * PI)); };
     auto m = MeshBuilder<Mesh>().newMesh(nx, ny).setMeshOfDim(0, sx).setMeshOfDim(1, sy).build();
+    g_mesh = &m;
     auto mk = [&](LocOnMesh l0, LocOnMesh l1) {
         return ExprBuilder<Field>().setMesh(m).setBC(0, DimPos::start, BCType::Neum, 0.).setBC(0, DimPos::end, BCType::Neum, 0.)
                 .setBC(1, DimPos::start, BCType::Neum, 0.).setBC(1, DimPos::end, BCType::Neum, 0.).setExt(2).setLoc({l0, l1}).build();

@@ -4,7 +4,7 @@
 // GMRES + PFMG, tol 1e-10) on n x n nodes, i.e. (n-1)^2 pressure cells, with the manufactured right-hand side
 // b = L_h(cos(2 pi x) cos(pi y)).  Prints one JSON line: milliseconds of the first solve (matrix assembly + HYPRE setup) and of
 // the following ones, iterations, relative residual; --dump writes p.
-//   ref_poisson --n N --solves S --threads T --dump path
+//   ref_poisson --n N --solves S --threads T --tol 1e-10 --dump path
 #include "ref_common.hpp"
 using namespace OpFlow;
 using namespace refdrv;
@@ -15,6 +15,7 @@ int main(int argc, char** argv) {
     const int solves = atoi(arg(argc, argv, "--solves", "3"));
     const int nt = atoi(arg(argc, argv, "--threads", "1"));
     const char* dump = arg(argc, argv, "--dump", "");
+    const double tol = atof(arg(argc, argv, "--tol", "1e-10"));
     set_threads(nt);
     using Mesh = CartesianMesh<Meta::int_<2>>;
     using Field = CartesianField<Real, Mesh>;
@@ -27,7 +28,7 @@ int main(int argc, char** argv) {
     pt.initBy([&](auto&& x) { return std::cos(2 * PI * x[0]) * std::cos(PI * x[1]); });
     b = d2x<D2SecondOrderCentered>(pt) + d2y<D2SecondOrderCentered>(pt);
     StructSolverParams<StructSolverType::GMRES> params;
-    params.tol = 1e-10;
+    params.tol = tol;
     params.maxIter = 100;
     params.staticMat = true;
     params.pinValue = true;

@@ -167,3 +167,62 @@ def test_host_access_semantics_program():
     authoring container with the oracle/build_ref.sh flags) -- here built against the B200 front-end"""
     r = run("fe_hostaccess", mode="exact")
     assert r.stdout.strip().endswith("PASS"), r.stdout[-2000:]
+
+
+def test_ops_driver_reproduces_reference_json():
+    """oracle/ref_drivers/ref_ops.cpp (flux-limiter interpolators of all ten schemes in both directions, 3x3 and 5x3 convolutions)
+    compiled against the B200 front-end: in EXACT mode its output -- ranges, locations and every value as a hex double -- is the
+    byte-for-byte document the unmodified reference printed (tests/golden/ref_ops.json); FAST within 1e-12"""
+    ref_txt = open(os.path.join(GOLD, "ref_ops.json")).read()
+    assert run("fe_ops", mode="exact").stdout == ref_txt
+    got, ref = json.loads(run("fe_ops", mode="fast").stdout), json.loads(ref_txt)
+    for g, r in zip(got["cases"], ref["cases"]):
+        assert g["acc"] == r["acc"] and g["loc"] == r["loc"]
+        a, b = (np.array([float.fromhex(v) for v in c["val"]]) for c in (g, r))
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), g["node"]
+
+
+def test_poisson_driver_matches_reference_solution(tmp_path):
+    """oracle/ref_drivers/ref_poisson.cpp (config C4's pressure handler: Neumann, pinValue, staticMat, GMRES + PFMG request) at 256^2
+    cells against the solution the unmodified reference computed with HYPRE (both driven to 1e-13): <= 1e-10 relative"""
+    out = str(tmp_path / "p.opfd")
+    r = run("fe_poisson", "--n", 257, "--solves", 2, "--tol", "1e-13", "--dump", out, mode="fast")
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["relerr"] <= 1e-12, info
+    _, _, got = O.read_opfd(out)
+    _, _, ref = O.read_opfd(os.path.join(GOLD, "poisson_n257.opfd"))
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 1e-10, f"pressure differs by {err:.3e} relative"
+
+
+def test_reference_example_ftcs_mpi_unchanged(tmp_path):
+    """examples/FTCS2D/FTCS-MPI.cpp compiled unchanged, run as a single worker (its set-up on 2 GPUs is covered bit-exactly by
+    tests/test_gpu_multi.py through the shared driver source): it must run to completion and write its output"""
+    exe = os.path.join(BIN, "ref_FTCS-MPI")
+    if not os.path.exists(exe):
+        pytest.skip("reference tree was not available when the front-end programs were built")
+    r = run("ref_FTCS-MPI", cwd=tmp_path, timeout=1800)
+    assert r.returncode == 0
+
+
+@pytest.mark.parametrize("mode,tol_uvw,tol_p", [("exact", 1e-9, 1e-8), ("fast", 1e-9, 1e-8)])
+def test_taylor_green_3d_matches_reference(tmp_path, mode, tol_uvw, tol_p):
+    """BASELINE config C5's program (oracle/ref_drivers/ref_tg3d.cpp: LidDriven3D.cpp's operator set and time step on the periodic
+    Taylor-Green box) at 32^3 cells, 1 + 2 steps, against the run of the unmodified reference (HYPRE GMRES / PCG + PFMG), all solves
+    driven to 1e-12: velocities and pressure agree to the accumulated solver tolerance (three semi-implicit momentum solves, the
+    explicit corrections, the pinned periodic Poisson solve and the projection per step)"""
+    exe = os.path.join(BIN, "fe_tg3d")
+    if not os.path.exists(exe):
+        pytest.skip("fe_tg3d not built (make -C tests/frontend tg3d: ~30 minutes of nvcc)")
+    pre = str(tmp_path / "tg")
+    r = run("fe_tg3d", "--n", 33, "--steps", 2, "--tol", "1e-12", "--dump", pre, mode=mode, timeout=1800)
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["cells"] == 32 ** 3
+    for name, tol in (("u", tol_uvw), ("v", tol_uvw), ("w", tol_uvw), ("p", tol_p)):
+        _, _, got = O.read_opfd(pre + f"_{name}.opfd")
+        _, _, ref = O.read_opfd(os.path.join(GOLD, f"tg3d_n33_s2_{name}.opfd"))
+        scale = max(np.abs(ref).max(), 1e-3)
+        if name == "p":
+            got, ref = got - got.mean(), ref - ref.mean()
+        err = np.abs(got - ref).max() / scale
+        assert err <= tol, f"{name}: relative L-inf difference {err:.3e} > {tol}"
