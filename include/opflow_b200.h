@@ -196,6 +196,11 @@ int opf_assign(opf_field_t dst, int op, const char* signature, const opf_field_t
 #define OPF_ASSIGN_NO_PADDING 1
 int opf_assign_ex(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields,
                   const double* scalars, int nscalars, int flags);
+/* `count` consecutive identical assignments -- a time loop whose body is this one statement (examples/FTCS2D/FTCS-OMP.cpp:24-27) --
+ * replayed from a CUDA graph of 32 steps each (captured once per destination / expression / operands / mode): removes the launch
+ * gaps that bound small fields (BASELINE config C1: 1025^2).  Results are identical to calling opf_assign `count` times. */
+int opf_assign_repeat(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars,
+                      int nscalars, int count);
 /* The same assignment for callers whose data lives in HOST memory (pinned for full speed): the values of `in_field` over its
  * localRange come from host_in (axis 0 fastest, dense), dst (op)= expr is evaluated, and dst's localRange is written to host_out.
  * in_field is dst itself or one of the expression's leaves; its ghost cells (BC extension, periodic images, halo planes of a

@@ -126,6 +126,7 @@ SIGNATURES = {
     "opf_expr_prepare": (C.c_int, [C.c_char_p, C.POINTER(_V), C.c_int, C.c_int, _R, _I]),
     "opf_assign": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int]),
     "opf_assign_ex": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int]),
+    "opf_assign_repeat": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int]),
     "opf_assign_host": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, _V, C.c_void_p, C.c_void_p]),
     "opf_solver_create": (_V, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_uint, C.POINTER(SolverParams)]),
     "opf_solver_solve": (C.c_int, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.POINTER(SolveState)]),

@@ -657,6 +657,9 @@ namespace OpFlow {
     struct BCInfo {// what ExprBuilder::setBC records per side (BC objects of src/Core/BC/*.hpp reduce to this on the device)
         BCType type = BCType::Undefined;
         Real value = 0;
+        // FunctorDircBC / FunctorNeumBC (DircBC.hpp:83-118, NeumBC.hpp): value as a function of the (ghost or boundary) cell index,
+        // type-erased over the index type; evaluated once on the host when the field is built (opf_bc_desc.face)
+        std::function<Real(const int*)> functor;
         BCType getBCType() const { return type; }
     };
 
@@ -912,6 +915,24 @@ namespace OpFlow {
             (pos == DimPos::start ? f.bc[d].start : f.bc[d].end) = BCInfo {type, static_cast<Real>(val)};
             return *this;
         }
+        // functor BC: setBC(d, pos, BCType::Dirc | Neum, [](auto&& index) { ... }) (CartesianField.hpp:870-892)
+        template <typename Fn>
+        requires(!Meta::Numerical<Fn> && requires(Fn fn, DS::MDIndex<dim> i) {
+            { fn(i) } -> std::convertible_to<Real>;
+        }) auto& setBC(int d, DimPos pos, BCType type, Fn&& functor) {
+            if (type != BCType::Dirc && type != BCType::Neum) {
+                OP_ERROR("BC Type not supported.");
+                OP_ABORT;
+            }
+            BCInfo info {type, 0.};
+            info.functor = [fn = std::decay_t<Fn>(std::forward<Fn>(functor))](const int* idx) {
+                DS::MDIndex<dim> i;
+                for (int k = 0; k < dim; ++k) i[k] = idx[k];
+                return static_cast<Real>(fn(i));
+            };
+            (pos == DimPos::start ? f.bc[d].start : f.bc[d].end) = std::move(info);
+            return *this;
+        }
         auto& setExt(int d, DimPos pos, int width) {
             (pos == DimPos::start ? f.ext_width[d].start : f.ext_width[d].end) = width;
             return *this;
@@ -953,6 +974,38 @@ namespace OpFlow {
                 d.n_ranks = (int) split.size();
                 d.rank = getWorkerId();
                 d.split_map = split.data();
+            }
+            // functor BCs: one value per index of the face slab -- the ghost layers of that side plus the boundary node / cell row,
+            // over the whole logical extent of the other axes (where updatePadding evaluates bc->evalAt(index),
+            // CartesianField.hpp:351-606).  The slab comes from a device-free plan of the same description.
+            std::vector<std::vector<double>> faces;
+            bool any_functor = false;
+            for (int k = 0; k < dim; ++k) any_functor = any_functor || f.bc[k].start.functor || f.bc[k].end.functor;
+            if (any_functor) {
+                opf_field_t plan = internal::check_ptr(opf_field_plan(&d, f.name.c_str()), "opf_field_plan");
+                opf_range logical, acc;
+                internal::check_rc(opf_field_get_range(plan, 3, &logical), "opf_field_get_range");
+                internal::check_rc(opf_field_get_range(plan, 2, &acc), "opf_field_get_range");
+                opf_field_destroy(plan);
+                faces.reserve(2 * dim);
+                for (int k = 0; k < dim; ++k)
+                    for (int side = 0; side < 2; ++side) {
+                        const BCInfo& b = side == 0 ? f.bc[k].start : f.bc[k].end;
+                        if (!b.functor) continue;
+                        opf_range fr = logical;
+                        for (int a = dim; a < OPF_MAX_DIM; ++a) fr.start[a] = 0, fr.end[a] = 1;
+                        if (side == 0) fr.end[k] = acc.start[k] + 1;
+                        else
+                            fr.start[k] = acc.end[k] - 1;
+                        std::vector<double> vals;
+                        int idx[OPF_MAX_DIM] = {0, 0, 0};
+                        for (idx[2] = fr.start[2]; idx[2] < fr.end[2]; ++idx[2])
+                            for (idx[1] = fr.start[1]; idx[1] < fr.end[1]; ++idx[1])
+                                for (idx[0] = fr.start[0]; idx[0] < fr.end[0]; ++idx[0]) vals.push_back(b.functor(idx));
+                        faces.push_back(std::move(vals));
+                        d.bc[k][side].face = faces.back().data();
+                        d.bc[k][side].face_range = fr;
+                    }
             }
             if (f.h) opf_field_destroy(f.h);
             f.h = internal::check_ptr(opf_field_create(&d, f.name.c_str()), "opf_field_create");

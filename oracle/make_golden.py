@@ -27,6 +27,7 @@ EXPLICIT = [  # (fixture name, ref_explicit arguments)
     ("upwind1_n101_s100", ["--case", "upwind1", "--n", 101, "--steps", 100, "--ghosts", 1]),
     ("weno_down_n129_sin_s30", ["--case", "weno_down", "--n", 129, "--steps", 30, "--ghosts", 1, "--init", "sin"]),
     ("ftcs2d_mpi_n65_sin_s200", ["--case", "ftcs2d_mpi", "--n", 65, "--steps", 200, "--init", "sin", "--ghosts", 1]),
+    ("ftcs2d_fbc_n41_sin_s60", ["--case", "ftcs2d_fbc", "--n", 41, "--steps", 60, "--init", "sin", "--ghosts", 1]),
 ]
 
 

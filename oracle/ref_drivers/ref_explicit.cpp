@@ -4,7 +4,7 @@
 // examples/FTCS2D/FTCS-OMP.cpp:26 (C1), its d2z extension (C2) and examples/CONV1D/CONV1D.cpp:29-31
 // with D1WENO53Downwind/Upwind or D1FirstOrderBiasedDownwind (C3).
 //
-//   ref_explicit --case ftcs2d|ftcs3d|ftcs2d_mpi|weno_down|weno_up|upwind1 --n N --steps S --warmup W
+//   ref_explicit --case ftcs2d|ftcs3d|ftcs2d_mpi|ftcs2d_fbc|weno_down|weno_up|upwind1 --n N --steps S --warmup W
 //                --threads T --init zero|sin --dump path --ghosts 0|1
 #include "ref_common.hpp"
 using namespace OpFlow;
@@ -70,6 +70,28 @@ int main(int argc, char** argv) {
         for (int i = 0; i < steps; ++i) step();
         double t1 = now();
         finish("ftcs3d", n, steps, nt, t1 - t0, (long long) (n - 2) * (n - 2) * (n - 2), u, dump, ghosts);
+    } else if (cs == "ftcs2d_fbc") {
+        // functor boundary conditions (setBC(d, pos, type, functor), CartesianField.hpp:870-892; FunctorDircBC DircBC.hpp:83-118):
+        // Dirichlet values varying along the x faces, a Neumann flux varying along the upper y face, a constant on the lower one
+        using Mesh = CartesianMesh<Meta::int_<2>>;
+        using Field = CartesianField<Real, Mesh>;
+        auto mesh = MeshBuilder<Mesh>().newMesh(n, n).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 2.).build();
+        const Real h = 2. / (n - 1);
+        auto u = ExprBuilder<Field>().setName("u").setMesh(mesh)
+                         .setBC(0, DimPos::start, BCType::Dirc, [=](auto&& i) { return 1. + 0.5 * std::sin(3. * h * i[1]); })
+                         .setBC(0, DimPos::end, BCType::Dirc, [=](auto&& i) { return 0.25 * h * i[1]; })
+                         .setBC(1, DimPos::start, BCType::Dirc, 0.75)
+                         .setBC(1, DimPos::end, BCType::Neum, [=](auto&& i) { return std::cos(0.5 * h * i[0]); })
+                         .setLoc(std::array {LocOnMesh::Center, LocOnMesh::Center}).setExt(1).build();
+        if (init == "sin") u.initBy([](auto&& x) { return std::sin(PI * x[0]) * std::sin(PI * x[1]); });
+        else u = 0;
+        const Real dt = 0.1 / Math::pow2(n - 1), alpha = 1.0;
+        auto step = [&] { u = u + dt * alpha * (d2x<D2SecondOrderCentered>(u) + d2y<D2SecondOrderCentered>(u)); };
+        for (int i = 0; i < warm; ++i) step();
+        double t0 = now();
+        for (int i = 0; i < steps; ++i) step();
+        double t1 = now();
+        finish("ftcs2d_fbc", n, steps, nt, t1 - t0, (long long) (n - 1) * (n - 1), u, dump, ghosts);
     } else if (cs == "ftcs2d_mpi") {
         // the set-up of examples/FTCS2D/FTCS-MPI.cpp:12-40: cell-centred field, ext 1, padding 1, EvenSplitStrategy over the
         // distributed workers of the global plan (one worker here for the reference build; N GPUs for the B200 front-end)

@@ -88,7 +88,7 @@ def test_explicit_fixtures(engine, mode, exact):
     host.set_mode(mode)
     man = json.load(open(os.path.join(GOLD, "manifest.json")))
     for name, info in man.items():
-        if "_mpi" in name:  # decomposed set-up: driven through the C++ front-end (tests/test_gpu_frontend.py, tests/test_gpu_multi.py)
+        if "_mpi" in name or "_fbc" in name:  # decomposed set-up / functor BCs: driven through the C++ front-end (tests/test_gpu_frontend.py, tests/test_gpu_multi.py)
             continue
         a = dict(zip(info["args"][::2], info["args"][1::2]))
         case, n, steps, init = a["--case"], int(a["--n"]), int(a["--steps"]), a.get("--init", "zero")
