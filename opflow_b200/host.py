@@ -158,7 +158,7 @@ def unary(node, e):
 
 
 def binary(node, a, b):
-    assert node in _BINARY_NODES + ["Min", "Max", "Add", "Sub", "Mul", "Div"], node
+    assert node in _BINARY_NODES + ["Min", "Max", "Add", "Sub", "Mul", "Div", "Lt", "Le", "Gt", "Ge", "Eq", "Ne", "And", "Or"], node
     return Expr(node, (_wrap(a), _wrap(b)))
 
 

@@ -388,6 +388,8 @@ static int parse_node(otree* t) {
 
 
 static int is(const onode* n, const char* s) { return !strcmp(n->name, s); }
+/* flux-limiter node: Fl<Scheme>C2N / Fl<Scheme>N2C (not "Floor") */
+static int is_fl(const onode* n, const char* dir) { return !strncmp(n->name, "Fl", 2) && strlen(n->name) > 5 && !strcmp(n->name + strlen(n->name) - 3, dir); }
 
 static void inherit(onode* n, const onode* a) {
     n->scalar = a->scalar;
@@ -440,14 +442,14 @@ static int prepare(otree* t, int id, orc_field** fields) {
         inherit(n, &t->n[n->child[0]]);
         n->loc[d] = LOC_CENTER;
         n->acc.end[d]--, n->logical.end[d]--, n->local.end[d]--;
-    } else if (!strncmp(n->name, "Fl", 2) && strstr(n->name, "C2N")) {/* D1FluxLimiter.hpp:155-171: props from arg2 */
+    } else if (is_fl(n, "C2N")) {/* D1FluxLimiter.hpp:155-171: props from arg2 */
         if (t->n[n->child[1]].loc[d] != LOC_CENTER) return 2;
         inherit(n, &t->n[n->child[1]]);
         n->loc[d] = LOC_CORNER;
         n->acc.start[d] += 2, n->acc.end[d] -= 1;
         n->local.start[d] += 2, n->local.end[d] -= 1;
         n->logical.start[d] += 2, n->logical.end[d] -= 1;
-    } else if (!strncmp(n->name, "Fl", 2) && strstr(n->name, "N2C")) {/* D1FluxLimiter.hpp:188-203 */
+    } else if (is_fl(n, "N2C")) {/* D1FluxLimiter.hpp:188-203 */
         if (t->n[n->child[1]].loc[d] != LOC_CORNER) return 2;
         inherit(n, &t->n[n->child[1]]);
         n->loc[d] = LOC_CENTER;
@@ -551,10 +553,10 @@ static double eval(const ectx* c, int id, const int* g) {
     int gm[3] = {g[0], g[1], g[2]}, gp[3] = {g[0], g[1], g[2]};
     if (is(n, "F")) return f_get(c->fields[n->leaf], g);
     if (is(n, "S")) return c->scalars[n->leaf];
-    if (!strncmp(n->name, "Fl", 2)) {/* D1FluxLimiterImpl::eval (D1FluxLimiter.hpp:148-151,182-185) */
+    if (is_fl(n, "C2N") || is_fl(n, "N2C")) {/* D1FluxLimiterImpl::eval (D1FluxLimiter.hpp:148-151,182-185) */
         const char* k = n->name + 2;
         const orc_mesh* m = c->m;
-        const int q = g[d], e = n->child[1], c2n = strstr(n->name, "C2N") != NULL;
+        const int q = g[d], e = n->child[1], c2n = is_fl(n, "C2N");
         const double uv = eval(c, n->child[0], g);
         double y[5];
         int o, gg[3] = {g[0], g[1], g[2]};

@@ -80,10 +80,14 @@ def test_against_oracle_random(engine, oracle, mode, exact, scheme):
         # Harmonic / Albada divide by r + 1 resp. r^2 + 1 with r = slope ratio of random data: wide dynamic range -> compare per
         # cell against the cell's own scale in FAST mode
         a, b = dst.to_numpy(r), od.view(r.tup(2))
+        # Harmonic is 0 / 0 where the two slopes cancel exactly (r = -1; it happens in mirrored Neumann ghost rows): the reference
+        # produces NaN there and so must the device, at the same cells
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{scheme} {direction}: NaN pattern differs"
+        ok = ~np.isnan(b)
         if exact:
-            assert np.array_equal(a, b), f"{scheme} {direction}"
+            assert np.array_equal(a[ok], b[ok]), f"{scheme} {direction}"
         else:
-            assert (np.abs(a - b) <= 1e-12 * np.maximum(np.abs(b), 1.0)).all(), f"{scheme} {direction}: {np.abs(a - b).max()}"
+            assert (np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(np.abs(b[ok]), 1.0)).all(), f"{scheme} {direction}: {np.abs(a[ok] - b[ok]).max()}"
 
 
 @pytest.mark.parametrize("mode,exact", MODES)
