@@ -150,6 +150,15 @@ int opf_field_upload(opf_field_t f, const opf_range* range, const double* host);
 int opf_field_download(opf_field_t f, const opf_range* range, double* host);
 /* assignImpl_final(const D&) CartesianField.hpp:237-280: field (op)= c over assignable∩local, then updatePadding */
 int opf_field_assign_scalar(opf_field_t f, int op, double c);
+/* Asynchronous snapshot for writers (reference: the `<<` of src/Utils/Writers/{RawBinaryStream,HDF5Stream,TecplotASCIIStream}.hpp reads
+ * the field on the host; here the values of `range` -- default localRange -- as of this point of the program are packed on the
+ * device and copied to `pinned_host` (opf_host_alloc) on a copy stream while the caller goes on; dense, axis 0 fastest).
+ * opf_snapshot_wait blocks until the host buffer is complete and releases the handle. */
+typedef struct opf_snapshot_s* opf_snapshot_t;
+void* opf_host_alloc(unsigned long long bytes); /* pinned host memory */
+int opf_host_free(void* p);
+opf_snapshot_t opf_field_snapshot(opf_field_t f, const opf_range* range, double* pinned_host);
+int opf_snapshot_wait(opf_snapshot_t s);
 /* assignImpl_final(const CartesianField&) :180-193: dst (op)= src (both initialised) */
 int opf_field_assign_field(opf_field_t dst, int op, opf_field_t src);
 /* updatePaddingImpl_final CartesianField.hpp:349-769: step 0 corner-Dirichlet nodes, step 1 BC ghost extension,

@@ -112,6 +112,10 @@ SIGNATURES = {
     "opf_field_device_ptr": (C.c_int, [_V, C.POINTER(_D), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "opf_field_upload": (C.c_int, [_V, _R, _V]),
     "opf_field_download": (C.c_int, [_V, _R, _V]),
+    "opf_host_alloc": (_V, [C.c_ulonglong]),
+    "opf_host_free": (C.c_int, [_V]),
+    "opf_field_snapshot": (_V, [_V, _R, _V]),
+    "opf_snapshot_wait": (C.c_int, [_V]),
     "opf_field_assign_scalar": (C.c_int, [_V, C.c_int, C.c_double]),
     "opf_field_assign_field": (C.c_int, [_V, C.c_int, _V]),
     "opf_field_update_padding": (C.c_int, [_V]),

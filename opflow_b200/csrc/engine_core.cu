@@ -1206,6 +1206,71 @@ int opf_field_download(opf_field_t f, const opf_range* range, double* host) {
     return copy_box(f, r, host, false);
 }
 
+
+// ---- asynchronous snapshots for writers ("stream writers with async D2H so the examples' output cadence does not stall
+// the pipeline"; reference: the writers of src/Utils/Writers/*.hpp read the field element by element on the host).  The box is packed
+// into a dense device buffer in stream order -- so it holds the values as of this point of the program, later assignments do not
+// disturb it -- and travels to pinned host memory on a separate copy stream; the caller's thread returns at once.
+struct opf_snapshot_s {
+    cudaEvent_t done = nullptr;
+    double* staging = nullptr;
+};
+static cudaStream_t snapshot_stream() {
+    static cudaStream_t st = nullptr;
+    if (!st) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    return st;
+}
+void* opf_host_alloc(unsigned long long bytes) {
+    void* p = nullptr;
+    if (require_device()) return nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) {
+        fail(OPF_ERR_CUDA, "cudaMallocHost(%llu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+int opf_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return OPF_OK;
+}
+opf_snapshot_t opf_field_snapshot(opf_field_t f, const opf_range* range, double* pinned_host) {
+    if (!f || !pinned_host || !f->buf[0]) {
+        fail(OPF_ERR_INVALID, "opf_field_snapshot: null argument or plan-only field");
+        return nullptr;
+    }
+    Context& c = ctx();
+    const Range r = range ? from_c(*range, f->dim) : f->local;
+    const long long n = r.count();
+    auto* s = new opf_snapshot_s();
+    if (cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming) != cudaSuccess || (n > 0 && cudaMalloc(&s->staging, sizeof(double) * n) != cudaSuccess)) {
+        fail(OPF_ERR_CUDA, "opf_field_snapshot: allocation failed");
+        delete s;
+        return nullptr;
+    }
+    if (n > 0) {
+        const long long n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1];
+        if (dense_convert(f, f->cur, s->staging, r, n0, n0 * n1, false, c.stream)) {
+            cudaFree(s->staging);
+            delete s;
+            return nullptr;
+        }
+        cudaEventRecord(c.ev_compute, c.stream);
+        cudaStreamWaitEvent(snapshot_stream(), c.ev_compute, 0);
+        cudaMemcpyAsync(pinned_host, s->staging, sizeof(double) * n, cudaMemcpyDeviceToHost, snapshot_stream());
+    }
+    cudaEventRecord(s->done, snapshot_stream());
+    return s;
+}
+int opf_snapshot_wait(opf_snapshot_t s) {
+    if (!s) return OPF_OK;
+    const cudaError_t e = cudaEventSynchronize(s->done);
+    cudaEventDestroy(s->done);
+    if (s->staging) cudaFree(s->staging);
+    delete s;
+    if (e != cudaSuccess) return fail(OPF_ERR_CUDA, "opf_snapshot_wait: %s", cudaGetErrorString(e));
+    return OPF_OK;
+}
+
 int opf_field_assign_scalar(opf_field_t f, int op, double c) {
     if (!f) return fail(OPF_ERR_INVALID, "null field");
     if (op < 0 || op > 4) return fail(OPF_ERR_UNSUPPORTED, "assign op %d is integer-only in the reference (Mod/And/Or/Xor/Shift)", op);

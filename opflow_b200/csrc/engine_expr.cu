@@ -3,6 +3,7 @@
 //   reference: src/Core/Expr/Expression.hpp:99-105 (prepare / contains), every Op::prepare (cited per node below),
 //              src/Core/Loops/FieldAssigner.hpp:26-86, src/Core/Loops/RangeFor.hpp:87-121.
 #include "engine.hpp"
+#include <array>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -393,6 +394,71 @@ namespace opfe {
             if (*p != ' ') k.push_back(*p);
         if (parse_signature(k.c_str(), t)) return 1;
         return std::max(1, node_radius(t, 0));
+    }
+
+
+    // offsets (relative to the evaluated cell) at which an expression reads its UNKNOWN leaves (mask bit k <=> field leaf k): the
+    // footprint of the matrix row the expression stands for.  Location-dependent stencils (D1C) are taken at their widest.
+    static void unknown_taps(const Tree& t, int id, unsigned mask, const std::vector<std::array<int, 3>>& at, std::vector<std::array<int, 3>>& out) {
+        const Node& n = t.nodes[id];
+        if (n.kind == K_F) {
+            if ((mask >> n.leaf) & 1u) out.insert(out.end(), at.begin(), at.end());
+            return;
+        }
+        if (n.kind == K_S) return;
+        auto shifted = [&](int axis, int lo, int hi) {
+            std::vector<std::array<int, 3>> r;
+            for (const auto& o : at)
+                for (int d = lo; d <= hi; ++d) {
+                    auto q = o;
+                    q[axis] += d;
+                    r.push_back(q);
+                }
+            std::sort(r.begin(), r.end());
+            r.erase(std::unique(r.begin(), r.end()), r.end());
+            return r;
+        };
+        switch (n.kind) {
+            case K_D2C: case K_D1C: return unknown_taps(t, n.child[0], mask, shifted(n.axis, -1, 1), out);
+            case K_D1DN: case K_INTPC2N: return unknown_taps(t, n.child[0], mask, shifted(n.axis, -1, 0), out);
+            case K_D1UP: case K_INTPN2C: return unknown_taps(t, n.child[0], mask, shifted(n.axis, 0, 1), out);
+            case K_WENODN: return unknown_taps(t, n.child[0], mask, shifted(n.axis, -3, 2), out);
+            case K_WENOUP: return unknown_taps(t, n.child[0], mask, shifted(n.axis, -2, 3), out);
+            case K_FLC2N:
+                unknown_taps(t, n.child[0], mask, at, out);
+                return unknown_taps(t, n.child[1], mask, shifted(n.axis, -2, 1), out);
+            case K_FLN2C:
+                unknown_taps(t, n.child[0], mask, at, out);
+                return unknown_taps(t, n.child[1], mask, shifted(n.axis, -1, 2), out);
+            case K_CONV: {
+                std::vector<std::array<int, 3>> r = at;
+                for (int d = 0; d < 3; ++d) {
+                    std::vector<std::array<int, 3>> q;
+                    for (const auto& o : r)
+                        for (int k = -n.conv[d] / 2; k <= n.conv[d] / 2; ++k) {
+                            auto v = o;
+                            v[d] += k;
+                            q.push_back(v);
+                        }
+                    r.swap(q);
+                }
+                return unknown_taps(t, n.child[0], mask, r, out);
+            }
+            default:
+                for (int c = 0; c < n.nchild; ++c) unknown_taps(t, n.child[c], mask, at, out);
+        }
+    }
+    int signature_unknown_taps(const char* sig, unsigned mask, std::vector<std::array<int, 3>>& out) {
+        Tree t;
+        std::string k;
+        for (const char* p = sig; *p; ++p)
+            if (*p != ' ') k.push_back(*p);
+        if (parse_signature(k.c_str(), t)) return 1;
+        out.clear();
+        unknown_taps(t, 0, mask, {{0, 0, 0}}, out);
+        std::sort(out.begin(), out.end());
+        out.erase(std::unique(out.begin(), out.end()), out.end());
+        return 0;
     }
 
     // ------------------------------------------------------------------------------------------ registry

@@ -22,6 +22,7 @@
 
 namespace opfe {
     int signature_radius(const char* sig);// engine_expr.cu
+    int signature_unknown_taps(const char* sig, unsigned mask, std::vector<std::array<int, 3>>& out);
     int reduce_sum_device(opf_field_s* f, const Range& r, double** dev_result);
     int dot_device(opf_field_s* a, opf_field_s* b, const Range& r, double* slot);
 }
@@ -307,17 +308,28 @@ namespace {
     }
 
     // probe vector for the diagonal: 1 on the cells whose index is congruent to `col` modulo m on every axis
+    // colour of a cell: cube colouring (i mod m0, j mod m1, k mod m2) == (c0, c1, c2), or -- lat[3] > 0 -- the lattice colouring
+    // (lat[0] i + lat[1] j + lat[2] k) mod lat[3] == c0
     struct Mod3 {
         int m[3];
+        int lat[4];
     };
+    __device__ __forceinline__ bool colour_on(const Mod3& mm, int dim, int i, int j, int k, int c0, int c1, int c2) {
+        if (mm.lat[3] > 0) {
+            long long v = (long long) mm.lat[0] * i + (dim >= 2 ? (long long) mm.lat[1] * j : 0) + (dim >= 3 ? (long long) mm.lat[2] * k : 0);
+            v %= mm.lat[3];
+            if (v < 0) v += mm.lat[3];
+            return (int) v == c0;
+        }
+        return ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1) && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
+    }
     __global__ void __launch_bounds__(256) color_fill_kernel(double* u, long long s1, long long s2, opf::LaunchRange r, int dim, Mod3 mm, int c0, int c1,
                                                              int c2) {
         {
             const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
             if (x0 >= r.hi[0] - r.lo[0]) return;
             const int i = r.lo[0] + x0, j = r.lo[1] + (int) blockIdx.y, k = r.lo[2] + (int) blockIdx.z;
-            const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
-                            && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
+            const bool on = colour_on(mm, dim, i, j, k, c0, c1, c2);
             u[(long long) i + (long long) j * s1 + (long long) k * s2] = on ? 1.0 : 0.0;
         }
     }
@@ -327,8 +339,7 @@ namespace {
             const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
             if (x0 >= r.hi[0] - r.lo[0]) return;
             const int i = r.lo[0] + x0, j = r.lo[1] + (int) blockIdx.y, k = r.lo[2] + (int) blockIdx.z;
-            const bool on = ((i % mm.m[0] + mm.m[0]) % mm.m[0] == c0) && (dim < 2 || (j % mm.m[1] + mm.m[1]) % mm.m[1] == c1)
-                            && (dim < 3 || (k % mm.m[2] + mm.m[2]) % mm.m[2] == c2);
+            const bool on = colour_on(mm, dim, i, j, k, c0, c1, c2);
             if (on) {
                 const long long o = (long long) i + (long long) j * s1 + (long long) k * s2;
                 const double d = q[o];
@@ -542,6 +553,9 @@ struct opf_solver_s {
     opf_field_s *X = nullptr, *B = nullptr, *R = nullptr, *P = nullptr, *Z = nullptr, *Q = nullptr;
     opf_field_s *R0 = nullptr, *V = nullptr, *S = nullptr, *T = nullptr, *E0 = nullptr;// BiCGSTAB extras, boundary-data field
     std::vector<opf_field_s*> gm_v;// GMRES basis (k + 1 vectors, allocated on first use)
+    int lattice[4] = {0, 0, 0, 0};   // probe colouring of the diagonal extraction: (a, b, c, M), found once
+    bool lattice_failed = false;
+    int solves = 0;                  // opf_solver_solve calls so far (lagged set-up of non-static operators)
     // an `lhs` that also carries terms without the unknown (the front-end passes  lhs(e) - rhs(e)  when both sides of `==`
     // contain e) is affine: lhs(p) = A.p + c.  C0 = lhs(0 with homogeneous BCs) = c is removed from every operator application.
     opf_field_s* C0 = nullptr;
@@ -654,7 +668,7 @@ namespace {
         const int dim = s->target->dim;
         const int m = 2 * signature_radius(s->lhs_sig.c_str()) + 1;
         // probe colouring: cells closer than the stencil width must differ in colour, also across a periodic seam
-        Mod3 mm{{1, 1, 1}};
+        Mod3 mm{{1, 1, 1}, {0, 0, 0, 0}};
         for (int d = 0; d < dim; ++d) {
             mm.m[d] = m;
             if (L.x->bc[d][0].type == OPF_BC_PERIODIC) {
@@ -662,8 +676,74 @@ namespace {
                 while (per % mm.m[d] != 0 && per % mm.m[d] < m && mm.m[d] < per) mm.m[d]++;
             }
         }
+        // Lattice colouring: cells i, j may share a probe iff no row reads both, i.e. i - j is not a difference of two footprint
+        // offsets.  colour = (a i + b j + c k) mod M separates them when a dx + b dy + c dz != 0 (mod M) for every such difference;
+        // the smallest M found (a brute-force search over M <= 128, once per solver) replaces the (2r+1)^dim cube: 27 -> 7 probes for
+        // the 7-point Laplacian, 125 -> ~20 for the semi-implicit momentum operators.  A periodic axis of extent N needs coef * N == 0
+        // (mod M) so that the colouring closes across the seam.
+        for (int q = 0; q < 4; ++q) mm.lat[q] = 0;
+        static const int lattice_on = getenv("OPF_DIAG_LATTICE") ? atoi(getenv("OPF_DIAG_LATTICE")) : 1;
+        if (lattice_on) {
+            if (s->lattice[3] == 0 && !s->lattice_failed) {
+                std::vector<std::array<int, 3>> taps;
+                bool found = false;
+                if (!signature_unknown_taps(s->lhs_sig.c_str(), s->mask, taps) && !taps.empty() && taps.size() <= 64) {
+                    std::vector<std::array<int, 3>> diff;
+                    for (const auto& p1 : taps)
+                        for (const auto& p2 : taps)
+                            if (p1 != p2) diff.push_back({p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]});
+                    std::sort(diff.begin(), diff.end());
+                    diff.erase(std::unique(diff.begin(), diff.end()), diff.end());
+                    long long per0[3] = {0, 0, 0};// periodic extents of the finest level (0: axis not periodic)
+                    for (int d = 0; d < dim; ++d)
+                        if (s->lv[0].x->bc[d][0].type == OPF_BC_PERIODIC) per0[d] = s->lv[0].x->accessible.end[d] - s->lv[0].x->accessible.start[d];
+                    for (int M = (int) taps.size(); M <= 96 && !found; ++M)
+                        for (int a = 1; a < std::min(std::max(2, M), 9) && !found; ++a)// a small first coefficient is enough in practice
+                            for (int b = (dim >= 2 ? 1 : 0); b < (dim >= 2 ? M : 1) && !found; ++b)
+                                for (int c = (dim >= 3 ? 1 : 0); c < (dim >= 3 ? M : 1) && !found; ++c) {
+                                    if ((a * per0[0]) % M || (b * per0[1]) % M || (c * per0[2]) % M) continue;
+                                    bool ok = true;
+                                    for (const auto& d : diff) {
+                                        long long v = ((long long) a * d[0] + (long long) b * d[1] + (long long) c * d[2]) % M;
+                                        if (v == 0) {
+                                            ok = false;
+                                            break;
+                                        }
+                                    }
+                                    if (ok) {
+                                        s->lattice[0] = a, s->lattice[1] = b, s->lattice[2] = c, s->lattice[3] = M;
+                                        found = true;
+                                    }
+                                }
+                }
+                if (!found) s->lattice_failed = true;
+            }
+            if (s->lattice[3] > 0) {
+                bool closes = true;// every level: periodic extents must be compatible with the lattice
+                const int coef[3] = {s->lattice[0], s->lattice[1], s->lattice[2]};
+                for (int d = 0; d < dim; ++d)
+                    if (L.x->bc[d][0].type == OPF_BC_PERIODIC) {
+                        const long long per = L.x->accessible.end[d] - L.x->accessible.start[d];
+                        if ((coef[d] * per) % s->lattice[3] != 0) closes = false;
+                    }
+                if (closes)
+                    for (int q = 0; q < 4; ++q) mm.lat[q] = s->lattice[q];
+            }
+        }
         const opf::LaunchRange r = lr_of(L.w);
         const BoxGrid bg = box_grid(L.w);
+        if (mm.lat[3] > 0) {
+            for (int col = 0; col < mm.lat[3]; ++col) {
+                color_fill_kernel<<<bg.grid, bg.block, 0, ctx().stream>>>(L.x->biased(L.x->cur), L.x->pitch1, L.x->pitch2, r, dim, mm, col, 0, 0);
+                ctx().launches++;
+                if (int rc = apply_lhs(s, L.x, L.q, level, false)) return rc;
+                color_recip_kernel<<<bg.grid, bg.block, 0, ctx().stream>>>(L.q->biased(L.q->cur), L.dinv->biased(L.dinv->cur), L.dinv->pitch1, L.dinv->pitch2, r, dim, mm,
+                                                                           col, 0, 0);
+                ctx().launches++;
+            }
+            OPF_CUDA(cudaGetLastError());
+            return assign(L.x, "S<0>", {}, {0.0});
+        }
         for (int c2 = 0; c2 < mm.m[2]; ++c2)
             for (int c1 = 0; c1 < mm.m[1]; ++c1)
                 for (int c0 = 0; c0 < mm.m[0]; ++c0) {
@@ -1598,7 +1678,14 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
             s->affine = cmax != 0.0;
         }
     }
-    if (!s->setup_done || !s->params.static_mat) {
+    // A non-static operator (the reference re-assembles and re-sets-up HYPRE on every solve) only needs its PRECONDITIONER data here --
+    // the diagonal behind Jacobi / the smoothers; the operator itself is always applied with the current coefficient fields.  That
+    // diagonal is refreshed every OPF_DIAG_REFRESH-th solve (default 8): a lagged diagonal changes iteration counts marginally, never
+    // the converged solution, and its extraction costs one operator application per probe colour.
+    static const int diag_refresh = getenv("OPF_DIAG_REFRESH") ? std::max(1, atoi(getenv("OPF_DIAG_REFRESH"))) : 8;
+    const bool refresh = !s->params.static_mat && (s->solves % diag_refresh == 0);
+    s->solves++;
+    if (!s->setup_done || refresh) {
         s->pin_active = false;
         // a multigrid request on an operator that cannot be coarsened (coefficient fields, decomposed target) degrades to its
         // level-0 smoother, i.e. Jacobi: the diagonal is needed then as well

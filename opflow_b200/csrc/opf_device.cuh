@@ -459,30 +459,55 @@ namespace opf {
     };
 
     // D1FirstOrderCentered<d>::eval (D1FirstOrderCentered.hpp:31-36); result loc flipped in prepare (:46)
+    // Fast arithmetic: the divides become multiplies by the per-axis reciprocal arrays (rdxh[i] = 1 / ((dx[i-1] + dx[i]) / 2))
+    template <class P, class Acc>
+    __device__ __forceinline__ double d1c_center(double e0, double em1, const Acc& m) {// Center -> Corner
+        if constexpr (P::fast) return (e0 - em1) * m.template rdxh<0>();
+        else return P::mul(P::div(P::sub(e0, em1), P::add(m.template dx<-1>(), m.template dx<0>())), 2.0);
+    }
+    template <class P, class Acc>
+    __device__ __forceinline__ double d1c_corner(double ep1, double e0, const Acc& m) {// Corner -> Center
+        if constexpr (P::fast) return (ep1 - e0) * m.template rdx<0>();
+        else return P::div(P::sub(ep1, e0), m.template dx<0>());
+    }
     template <int D, class E>
     struct D1C {
         OPF_STENCIL_HEAD(-1, 1)
         OPF_EVAL_BEGIN
-            if ((a.loc[B] >> D) & 1) return P::mul(P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), P::add(acc.template dx<-1>(), acc.template dx<0>())), 2.0);
-            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), acc.template dx<0>());
+            if ((a.loc[B] >> D) & 1) return d1c_center<P>(TAP(IC<0>{}), TAP(IC<-1>{}), acc);
+            return d1c_corner<P>(TAP(IC<1>{}), TAP(IC<0>{}), acc);
         }
         OPF_EV_BEGIN
-            if ((a.loc[B] >> D) & 1) return P::mul(P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), P::add(acc.template dx<-1>(), acc.template dx<0>())), 2.0);
-            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), acc.template dx<0>());
+            if ((a.loc[B] >> D) & 1) return d1c_center<P>(TAP(IC<0>{}), TAP(IC<-1>{}), acc);
+            return d1c_corner<P>(TAP(IC<1>{}), TAP(IC<0>{}), acc);
         }
     };
 
     // D1FirstOrderBiasedDownwind<d>::eval (D1FirstOrderBiasedDownwind.hpp:53-57)
+    template <class P, class Acc>
+    __device__ __forceinline__ double d1dn_math(double e0, double em1, bool center, const Acc& m) {
+        if constexpr (P::fast) return (e0 - em1) * (center ? m.template rdxh<0>() : m.template rdx<-1>());
+        else {
+            const double h = center ? P::mul(P::add(m.template dx<-1>(), m.template dx<0>()), 0.5) : m.template dx<-1>();
+            return P::div(P::sub(e0, em1), h);
+        }
+    }
+    template <class P, class Acc>
+    __device__ __forceinline__ double d1up_math(double ep1, double e0, bool center, const Acc& m) {
+        if constexpr (P::fast) return (ep1 - e0) * (center ? m.template rdxh<1>() : m.template rdx<0>());
+        else {
+            const double h = center ? P::mul(P::add(m.template dx<0>(), m.template dx<1>()), 0.5) : m.template dx<0>();
+            return P::div(P::sub(ep1, e0), h);
+        }
+    }
     template <int D, class E>
     struct D1Dn {
         OPF_STENCIL_HEAD(-1, 0)
         OPF_EVAL_BEGIN
-            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<-1>(), acc.template dx<0>()), 0.5) : acc.template dx<-1>();
-            return P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), h);
+            return d1dn_math<P>(TAP(IC<0>{}), TAP(IC<-1>{}), (a.loc[B] >> D) & 1, acc);
         }
         OPF_EV_BEGIN
-            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<-1>(), acc.template dx<0>()), 0.5) : acc.template dx<-1>();
-            return P::div(P::sub(TAP(IC<0>{}), TAP(IC<-1>{})), h);
+            return d1dn_math<P>(TAP(IC<0>{}), TAP(IC<-1>{}), (a.loc[B] >> D) & 1, acc);
         }
     };
     // D1FirstOrderBiasedUpwind<d>::eval (D1FirstOrderBiasedUpwind.hpp:54-58)
@@ -490,12 +515,10 @@ namespace opf {
     struct D1Up {
         OPF_STENCIL_HEAD(0, 1)
         OPF_EVAL_BEGIN
-            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<0>(), acc.template dx<1>()), 0.5) : acc.template dx<0>();
-            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), h);
+            return d1up_math<P>(TAP(IC<1>{}), TAP(IC<0>{}), (a.loc[B] >> D) & 1, acc);
         }
         OPF_EV_BEGIN
-            const double h = ((a.loc[B] >> D) & 1) ? P::mul(P::add(acc.template dx<0>(), acc.template dx<1>()), 0.5) : acc.template dx<0>();
-            return P::div(P::sub(TAP(IC<1>{}), TAP(IC<0>{})), h);
+            return d1up_math<P>(TAP(IC<1>{}), TAP(IC<0>{}), (a.loc[B] >> D) & 1, acc);
         }
     };
 
@@ -608,6 +631,11 @@ namespace opf {
     // D1Linear<d, Cen2Cor>::eval (D1Linear.hpp:36-42) with Interpolator1D::intp (Interpolator.hpp:21-23,38-40)
     template <class P, class Acc>
     __device__ __forceinline__ double intp_c2n(double y1, double y2, const Acc& m) {
+        if constexpr (P::fast) {
+            // x1 - x = -dx[-1] / 2 and x2 - x = +dx[0] / 2, so the interpolant is (dx[-1] y2 + dx[0] y1) / (dx[-1] + dx[0]): no divide,
+            // no coordinate loads (on a uniform axis: (y1 + y2) / 2 up to one rounding)
+            return (m.template dx<-1>() * y2 + m.template dx<0>() * y1) * (0.5 * m.template rdxh<0>());
+        }
         const double x1 = P::add(m.template x<-1>(), P::mul(0.5, m.template dx<-1>()));
         const double x2 = P::add(m.template x<0>(), P::mul(0.5, m.template dx<0>()));
         const double x = m.template x<0>();
@@ -934,8 +962,19 @@ namespace opf {
             return v;
         }
         static constexpr int XL = bound(0), XH = bound(1), CL = bound(2), CH = bound(3), ML = bound(4), MH = bound(5);
-        // cross offsets only exist in 3-D
-        static constexpr bool ok = !overflow && (DIM == 3 || DIM == 2);
+        // doubles a thread keeps live in its register window with CX = 2 cells per thread: every tapped column (slot, cross offset)
+        // holds its march extent + the prefetched row, each row CX + x-halo wide
+        __host__ __device__ static constexpr int live_doubles() {
+            int n = 0;
+            for (int s = 0; s < NS; ++s)
+                for (int dc = -WR; dc <= WR; ++dc)
+                    if (col_used(s, dc)) n += (col_mhi(s, dc) - col_mlo(s, dc) + 2) * (2 + col_xhi(s, dc) - col_xlo(s, dc));
+            return n;
+        }
+        // cross offsets only exist in 3-D.  Expressions whose window does not fit the register file (many operand fields: the
+        // semi-implicit momentum operators of LidDriven3D.cpp keep ~15 fields x 3-5 rows) take the direct-global skeleton: the window
+        // skeleton spilled ~2.9 KB of stack per thread on them and ran 3.5x slower (cuobjdump -res-usage; profiles/r2_c5.md)
+        static constexpr bool ok = !overflow && (DIM == 3 || DIM == 2) && live_doubles() <= 56 && E::size <= 48;
     };
 
     template <class E, bool A0, int DIM, int CX, bool UNI_ = false>

@@ -226,3 +226,23 @@ def test_taylor_green_3d_matches_reference(tmp_path, mode, tol_uvw, tol_p):
             got, ref = got - got.mean(), ref - ref.mean()
         err = np.abs(got - ref).max() / scale
         assert err <= tol, f"{name}: relative L-inf difference {err:.3e} > {tol}"
+
+
+def test_binary_streams_round_trip(tmp_path):
+    """tests/frontend/fe_io.cpp: RawBinaryOStream (.cart files in the reference's layout) and H5Stream written from asynchronous device
+    snapshots inside a time loop, read back by RawBinaryIStream / H5Stream(StreamIn): bit-identical; and the .cart header is the
+    reference's (RawBinaryStream.hpp:98-160: name, dim, nproc, time, mesh range, coordinates, accessible and local range)"""
+    import struct
+    os.makedirs(tmp_path / "out")
+    r = run("fe_io", cwd=tmp_path)
+    assert r.stdout.strip().endswith("PASS"), r.stdout[-500:] + r.stderr[-500:]
+    b = open(tmp_path / "out" / "u_2.cart", "rb").read()
+    n = struct.unpack_from("i", b, 0)[0]
+    assert b[4:4 + n] == b"u"
+    dim, nproc = struct.unpack_from("ii", b, 4 + n)
+    t = struct.unpack_from("d", b, 12 + n)[0]
+    assert (dim, nproc, t) == (2, 1, 2.0)
+    assert struct.unpack_from("4i", b, 20 + n) == (0, 33, 0, 17)
+    off = 20 + n + 16 + 8 * (33 + 17)
+    assert struct.unpack_from("8i", b, off) == (0, 33, 0, 17, 0, 33, 0, 17)
+    assert len(b) == off + 32 + 8 * 33 * 17
