@@ -36,6 +36,7 @@ namespace opfe {
             {"Pow2", K_POW2, 1, false},   {"Cond", K_COND, 3, false},   {"D2C", K_D2C, 1, true},      {"D1C", K_D1C, 1, true},
             {"D1Dn", K_D1DN, 1, true},    {"D1Up", K_D1UP, 1, true},    {"WenoDn", K_WENODN, 1, true}, {"WenoUp", K_WENOUP, 1, true},
             {"IntpC2N", K_INTPC2N, 1, true}, {"IntpN2C", K_INTPN2C, 1, true}, {"Conv", K_CONV, 1, false},
+            {"Adapt1", K_UNI, 1, false}, {"Adapt2", K_BIN, 2, false},// UniOpAdaptor / BinOpAdaptor<functor>: Adapt1<functorName,E>
             {"FlCentralC2N", K_FLC2N, 2, true}, {"FlCentralN2C", K_FLN2C, 2, true}, {"FlQuickC2N", K_FLC2N, 2, true}, {"FlQuickN2C", K_FLN2C, 2, true}, {"FlCuiC2N", K_FLC2N, 2, true}, {"FlCuiN2C", K_FLN2C, 2, true}, {"FlFrommC2N", K_FLC2N, 2, true}, {"FlFrommN2C", K_FLN2C, 2, true}, {"FlLuiC2N", K_FLC2N, 2, true}, {"FlLuiN2C", K_FLN2C, 2, true}, {"FlMinmodC2N", K_FLC2N, 2, true}, {"FlMinmodN2C", K_FLN2C, 2, true}, {"FlSuperbeeC2N", K_FLC2N, 2, true}, {"FlSuperbeeN2C", K_FLN2C, 2, true}, {"FlMusclC2N", K_FLC2N, 2, true}, {"FlMusclN2C", K_FLN2C, 2, true}, {"FlHarmonicC2N", K_FLC2N, 2, true}, {"FlHarmonicN2C", K_FLN2C, 2, true}, {"FlAlbadaC2N", K_FLC2N, 2, true}, {"FlAlbadaN2C", K_FLN2C, 2, true}, 
             {"Exp2", K_UNI, 1, false}, {"Expm1", K_UNI, 1, false}, {"Log10", K_UNI, 1, false}, {"Log2", K_UNI, 1, false}, {"Log1p", K_UNI, 1, false}, {"Cbrt", K_UNI, 1, false}, {"ASin", K_UNI, 1, false}, {"ACos", K_UNI, 1, false}, {"ATan", K_UNI, 1, false}, {"Sinh", K_UNI, 1, false}, {"Cosh", K_UNI, 1, false}, {"ASinh", K_UNI, 1, false}, {"ACosh", K_UNI, 1, false}, {"ATanh", K_UNI, 1, false}, {"Erf", K_UNI, 1, false}, {"Erfc", K_UNI, 1, false}, {"TGamma", K_UNI, 1, false}, {"LGamma", K_UNI, 1, false}, {"Ceil", K_UNI, 1, false}, {"Floor", K_UNI, 1, false}, {"Trunc", K_UNI, 1, false}, {"Round", K_UNI, 1, false}, {"LRound", K_UNI, 1, false}, {"LLRound", K_UNI, 1, false}, {"NearbyInt", K_UNI, 1, false}, {"Rint", K_UNI, 1, false}, {"LRint", K_UNI, 1, false}, {"LLRint", K_UNI, 1, false}, {"ILogb", K_UNI, 1, false}, {"Logb", K_UNI, 1, false}, {"FMod", K_BIN, 2, false}, {"Remainder", K_BIN, 2, false}, {"FDim", K_BIN, 2, false}, {"Hypot", K_BIN, 2, false}, {"ATan2", K_BIN, 2, false}, {"Ldexp", K_BIN, 2, false}, {"Scalbn", K_BIN, 2, false}, {"Scalbln", K_BIN, 2, false}, {"Nextafter", K_BIN, 2, false}, {"Nexttoward", K_BIN, 2, false}, {"Copysing", K_BIN, 2, false}};
 
@@ -108,6 +109,17 @@ namespace opfe {
                 else
                     t.nscalars = std::max(t.nscalars, v + 1);
             } else {
+                if (name == "Adapt1" || name == "Adapt2") {// the functor's name is part of the signature (registry key), not of the tree
+                    ws();
+                    const size_t b2 = pos;
+                    while ((s[pos] >= 'A' && s[pos] <= 'Z') || (s[pos] >= 'a' && s[pos] <= 'z') || (s[pos] >= '0' && s[pos] <= '9') || s[pos] == '_') ++pos;
+                    ws();
+                    if (pos == b2 || s[pos] != ',') {
+                        err = "Adapt<functorName, operands...> expected";
+                        return -1;
+                    }
+                    ++pos;
+                }
                 if (ki->kind == K_CONV) {// Conv<n0, n1, n2, k0, E>
                     for (int q = 0; q < 4; ++q) {
                         int v;

@@ -351,6 +351,45 @@ namespace opf {
     OPF_UNIOP(Logb, logb(x))
 #undef OPF_UNIOP
 
+    // UniOpAdaptor<functor> / BinOpAdaptor<functor> (src/Core/Operator/PerElemOpAdaptor.hpp:23-110): a user functor applied element by
+    // element.  Fn is the functor's TYPE (a NamedFunctor is a stateless constexpr object): it must be default-constructible and its
+    // call operator usable in device code -- `__host__ __device__`, or constexpr under nvcc's --expt-relaxed-constexpr.
+    template <class Fn, class E>
+    struct Adapt1 {
+        static constexpr int size = 1 + E::size, maxaxis = E::maxaxis, nf = E::nf;
+        template <int B, class P, bool A0>
+        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
+            return static_cast<double>(Fn {}(E::template eval<B + 1, P, A0>(a, i, j, k)));
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            return static_cast<double>(Fn {}(E::template ev<B + 1, P, A0, DI, DJ, DK>(c)));
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            E::template taps<A0>(ts, in);
+        }
+    };
+    template <class Fn, class L, class R>
+    struct Adapt2 {
+        static constexpr int size = 1 + L::size + R::size;
+        static constexpr int maxaxis = L::maxaxis > R::maxaxis ? L::maxaxis : R::maxaxis;
+        static constexpr int nf = L::nf > R::nf ? L::nf : R::nf;
+        template <int B, class P, bool A0>
+        __device__ __forceinline__ static double eval(const ExprArgs& a, int i, int j, int k) {
+            return static_cast<double>(Fn {}(L::template eval<B + 1, P, A0>(a, i, j, k), R::template eval<B + 1 + L::size, P, A0>(a, i, j, k)));
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class C>
+        __device__ __forceinline__ static double ev(const C& c) {
+            return static_cast<double>(Fn {}(L::template ev<B + 1, P, A0, DI, DJ, DK>(c), R::template ev<B + 1 + L::size, P, A0, DI, DJ, DK>(c)));
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS& ts, const TapGrid& in) {
+            L::template taps<A0>(ts, in);
+            R::template taps<A0>(ts, in);
+        }
+    };
+
     // CondOp::eval (Conditional.hpp:37-40)
     template <class Cc, class A, class Bb>
     struct Cond {
@@ -967,7 +1006,7 @@ namespace opf {
         __host__ __device__ static constexpr int live_doubles() {
             int n = 0;
             for (int s = 0; s < NS; ++s)
-                for (int dc = -WR; dc <= WR; ++dc)
+                for (int dc = (DIM == 3 ? -WR : 0); dc <= (DIM == 3 ? WR : 0); ++dc)// 2-D has no cross axis: one column per slot
                     if (col_used(s, dc)) n += (col_mhi(s, dc) - col_mlo(s, dc) + 2) * (2 + col_xhi(s, dc) - col_xlo(s, dc));
             return n;
         }

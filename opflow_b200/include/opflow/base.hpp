@@ -52,7 +52,16 @@ namespace OpFlow {
             for (int i = 0; i < e; ++i) r *= b;
             return r;
         }
-        inline double smoothHeviside(double eps, double d) {
+#if defined(__CUDACC__)
+#define OPF_HD __host__ __device__
+#else
+#define OPF_HD
+#endif
+        // Math/Function/Numeric.hpp:86-96; usable inside device functors (UniOpAdaptor of examples/LevelSet/UniLS.cpp:109-112)
+        OPF_HD inline double smoothDelta(double eps, double d) {
+            return (d > -d ? d : -d) > eps ? 0. : 1. / 2. / eps * (1 + std::cos(d * 3.141592653589793 / eps));
+        }
+        OPF_HD inline double smoothHeviside(double eps, double d) {
             if (d < -eps) return 0.;
             if (d > eps) return 1.;
             return 0.5 * (1. + d / eps + 1. / PI * std::sin(PI * d / eps));

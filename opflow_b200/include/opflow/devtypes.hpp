@@ -109,5 +109,7 @@ namespace opf {
     template <int D, class U, class E> struct FlAlbadaC2N;
     template <int D, class U, class E> struct FlAlbadaN2C;
     template <int N0, int N1, int N2, int K0, class E> struct Conv;
+    template <class Fn, class E> struct Adapt1;
+    template <class Fn, class L, class R> struct Adapt2;
 }// namespace opf
 #endif

@@ -168,7 +168,9 @@ namespace OpFlow {
         };
         void flatten(internal::Flat& fl) const {
             fl.sig += Op::name;
-            fl.sig += "<";
+            // adaptor ops carry "Adapt1<functorName" as their name: the operands follow after a comma
+            const bool adaptor = fl.sig.size() >= 1 && std::string_view(Op::name).find('<') != std::string_view::npos;
+            fl.sig += adaptor ? "," : "<";
             if constexpr (Op::axis >= 0) fl.sig += std::to_string(Op::axis) + ",";
             bool first = true;
             std::apply(
@@ -536,6 +538,107 @@ namespace OpFlow {
     using D1Harmonic = typename D1FluxLimiterGen<HarmonicKernel>::template Op<d, dir>;
     template <std::size_t d, IntpDirection dir>
     using D1Albada = typename D1FluxLimiterGen<vanAlbadaKernel>::template Op<d, dir>;
+
+    // ------------------------------------------------------------------------------------------------ element-wise functor adaptors
+    // Utils::NamedFunctor / makeCXprString (src/Utils/NamedFunctor.hpp:21-52, ConstexprString.hpp) and UniOpAdaptor / BinOpAdaptor
+    // (src/Core/Operator/PerElemOpAdaptor.hpp:23-110).  The functor runs inside the device kernels: its call operator must be usable in
+    // device code (a `__host__ __device__` function object, or a constexpr one under --expt-relaxed-constexpr).  Its name becomes part
+    // of the expression signature, so two functors never share a kernel.  nvcc cannot name a lambda's closure type in a kernel's
+    // template arguments, so the functor has to be an object of a NAMED type (struct SmoothDelta { OPF_HD double operator()(double) const; });
+    // the `constexpr auto func = [=](Real d) {...}` form of UniLS.cpp:109 compiles against the reference only.
+    namespace Utils {
+        template <std::size_t N>
+        struct CXprString {
+            char s[N] {};
+            constexpr CXprString(const char (&str)[N]) {
+                for (std::size_t i = 0; i < N; ++i) s[i] = str[i];
+            }
+            constexpr std::string to_string() const { return std::string(s); }
+        };
+        template <std::size_t N>
+        constexpr auto makeCXprString(const char (&str)[N]) {
+            return CXprString<N>(str);
+        }
+        template <auto Functor, auto Name>
+        struct NamedFunctor {
+            constexpr NamedFunctor() = default;
+            constexpr static auto getFunc() { return Functor; }
+            constexpr static auto getName() { return Name; }
+            template <typename... A>
+#if defined(__CUDACC__)
+            __host__ __device__
+#endif
+                    constexpr auto
+                    operator()(A&&... args) const {
+                return Functor(std::forward<A>(args)...);
+            }
+        };
+        template <typename T>
+        struct is_named_functor : std::false_type {};
+        template <auto F, auto N>
+        struct is_named_functor<NamedFunctor<F, N>> : std::true_type {};
+        template <typename T>
+        concept NamedFunctorType = is_named_functor<std::remove_cvref_t<T>>::value;
+    }// namespace Utils
+    namespace internal {
+        template <auto Functor>
+        inline const std::string adaptor_name = [] {
+            std::string n;
+            for (char c : Functor.getName().to_string())
+                if (c) n.push_back(std::isalnum((unsigned char) c) ? c : '_');
+            return n.empty() ? std::string("unnamed_functor") : n;
+        }();
+    }
+    template <Utils::NamedFunctorType auto Functor>
+    struct UniOpAdaptor {
+        static inline const std::string name_str = "Adapt1<" + internal::adaptor_name<Functor>;
+        static inline const char* name = name_str.c_str();// flatten() appends "<" after the op name: the functor name follows as "Adapt1<name,...": see below
+        static constexpr int axis = -1;
+        static constexpr int bc_width = 0;
+        template <class A>
+        using dev = opf::Adapt1<std::remove_cvref_t<decltype(Functor.getFunc())>, A>;
+    };
+    template <Utils::NamedFunctorType auto Functor>
+    struct BinOpAdaptor {
+        static inline const std::string name_str = "Adapt2<" + internal::adaptor_name<Functor>;
+        static inline const char* name = name_str.c_str();
+        static constexpr int axis = -1;
+        static constexpr int bc_width = 0;
+        template <class A, class B>
+        using dev = opf::Adapt2<std::remove_cvref_t<decltype(Functor.getFunc())>, A, B>;
+    };
+
+    // The nvcc-proof spelling: the functor is a named TYPE carrying its own name --
+    //   struct SmoothDelta { static constexpr const char* name = "smoothDelta"; OPF_HD double operator()(double d) const {...} };
+    //   auto delta = makeExpression<UniOpAdaptorT<SmoothDelta>>(p0);
+    // (nvcc 12.9 can carry neither a lambda's closure type nor a class-type non-type template argument -- NamedFunctor<func, name> is
+    // both -- through the host stubs of a kernel template, so UniOpAdaptor<functor> above only compiles in host-only builds.)
+    namespace internal {
+        template <typename Fn>
+        inline const std::string adaptor_type_name = [] {
+            std::string n;
+            for (const char* c = Fn::name; *c; ++c) n.push_back(std::isalnum((unsigned char) *c) ? *c : '_');
+            return n;
+        }();
+    }
+    template <typename Fn>
+    struct UniOpAdaptorT {
+        static inline const std::string name_str = "Adapt1<" + internal::adaptor_type_name<Fn>;
+        static inline const char* name = name_str.c_str();
+        static constexpr int axis = -1;
+        static constexpr int bc_width = 0;
+        template <class A>
+        using dev = opf::Adapt1<Fn, A>;
+    };
+    template <typename Fn>
+    struct BinOpAdaptorT {
+        static inline const std::string name_str = "Adapt2<" + internal::adaptor_type_name<Fn>;
+        static inline const char* name = name_str.c_str();
+        static constexpr int axis = -1;
+        static constexpr int bc_width = 0;
+        template <class A, class B>
+        using dev = opf::Adapt2<Fn, A, B>;
+    };
 
     // ------------------------------------------------------------------------------------------------ convolution
     // conv(expr, kernel) (Convolution.hpp:160-170): the kernel tensor's entries travel as consecutive scalar leaves (x fastest)

@@ -246,3 +246,16 @@ def test_binary_streams_round_trip(tmp_path):
     off = 20 + n + 16 + 8 * (33 + 17)
     assert struct.unpack_from("8i", b, off) == (0, 33, 0, 17, 0, 33, 0, 17)
     assert len(b) == off + 32 + 8 * 33 * 17
+
+
+def test_functor_adaptor_convolution_program(tmp_path):
+    """oracle/ref_drivers/ref_adapt.cpp (the volume-constraint step of UniLS.cpp:104-118: UniOpAdaptor of smoothDelta, pow, two 3 x 3
+    convolutions in one assignment) against the dump of the unmodified reference.  The functor calls cos and the expression calls
+    pow: CUDA's and glibc's libm agree to 1-2 ulp, not bit for bit, hence 1e-13 relative in both modes."""
+    out = str(tmp_path / "p.opfd")
+    _, _, ref = O.read_opfd(os.path.join(GOLD, "adapt_n65.opfd"))
+    for mode in ("exact", "fast"):
+        run("fe_adapt", "--dump", out, mode=mode)
+        _, _, got = O.read_opfd(out)
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err <= 1e-13, f"{mode}: relative L-inf difference {err:.3e}"
