@@ -223,3 +223,36 @@ def test_reductions(engine, oracle, dims):
     # dot product through an expression
     d = host.rangeReduce(g * g, capi.RED_SUM, r)
     assert abs(d - (ref * ref).sum()) <= 1e-12 * (ref * ref).sum()
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_EXACT, capi.MODE_FAST])
+@pytest.mark.parametrize("dims,count", [((129, 97), 100), ((65, 33, 17), 71), ((257,), 40)])
+def test_assign_repeat_equals_plain_assignments(engine, mode, dims, count):
+    """opf_assign_repeat (the time loop replayed from CUDA graphs of 32 steps) == the same number of plain assignments, bit for bit:
+    ping-pong buffers, BC fills and the remainder steps included; called twice so that the second call replays a cached graph"""
+    import ctypes as C
+    host.set_mode(mode)
+    dim = len(dims)
+    res = []
+    for use_repeat in (False, True):
+        g, _ = make_pair(list(dims), [0] * dim, [1] * dim, bc=dirc(dim))
+        rng = np.random.default_rng(9)
+        g.from_numpy(np.asfortranarray(rng.standard_normal(g.localRange.shape(dim))))
+        c = 0.05 / (max(dims) - 1) ** 2
+        lap = d2x(D2SecondOrderCentered, g)
+        if dim >= 2:
+            lap = lap + d2y(D2SecondOrderCentered, g)
+        if dim == 3:
+            lap = lap + d2z(D2SecondOrderCentered, g)
+        e = g + c * lap
+        sig, fields, scalars = e.flatten()
+        F = (C.c_void_p * len(fields))(*[f.h for f in fields])
+        S = (C.c_double * len(scalars))(*scalars)
+        for _ in range(2):
+            if use_repeat:
+                capi.check(engine.opf_assign_repeat(g.h, capi.OP_EQ, sig.encode(), F, len(fields), S, len(scalars), count))
+            else:
+                for _ in range(count):
+                    g.assign(e)
+        res.append(g.to_numpy(g.getLocalReadableRange()))
+    assert np.array_equal(res[0], res[1])
