@@ -458,6 +458,9 @@ def run_c2(env, args):
         sampler.start()
         time.sleep(1.0)  # the sampler's start-up (a driver query per GPU) stays out of the first timed batch
     env.barrier()
+    for _ in range(args.steps):  # one untimed batch with the sampler running: its first driver queries stall launches for tens of ms
+        step()
+    env.barrier()
     launches0 = l.opf_launch_count()
     step()
     launches_per_step = l.opf_launch_count() - launches0
