@@ -14,6 +14,7 @@
 #include <format>
 #include <fstream>
 #include <functional>
+#include <thread>
 #include <iostream>
 #include <memory>
 #include <numeric>
@@ -283,9 +284,44 @@ namespace OpFlow {
         }
         return std::forward<F>(func);
     }
+    namespace internal {
+        // shared-memory workers of the global plan (setGlobalParallelPlan, ParallelPlan.hpp:38-50); 1 by default, like the reference
+        inline int g_host_threads = 1;
+    }
+    // rangeFor (RangeFor.hpp:69-84): the reference hands the range to tbb::parallel_for with the plan's shared-memory worker count
+    // (1 unless the program asks for more).  Here: the slowest axis is cut into one contiguous piece per worker.  The first index runs
+    // on the calling thread before the workers start, so that lazily synchronised host mirrors of the fields the functor touches are
+    // in place (operator[] downloads on first access); like the reference, the functor must be safe to call concurrently.
     template <std::size_t d, typename F>
     F rangeFor(const DS::Range<d>& range, F&& func) {
-        return rangeFor_s(range, std::forward<F>(func));
+        const int nt = internal::g_host_threads;
+        const int total = range.count();
+        const int n_slow = range.end[d - 1] - range.start[d - 1];
+        if (nt <= 1 || total < 4096 || n_slow < 2 || range.stride[d - 1] != 1) return rangeFor_s(range, std::forward<F>(func));
+        {
+            DS::MDIndex<d> first {range.start};
+            func(first);
+        }
+        const int workers = std::min(nt, n_slow);
+        std::vector<std::thread> pool;
+        pool.reserve(workers);
+        for (int w = 0; w < workers; ++w) {
+            DS::Range<d> piece = range;
+            piece.start[d - 1] = range.start[d - 1] + (int) ((long long) n_slow * w / workers);
+            piece.end[d - 1] = range.start[d - 1] + (int) ((long long) n_slow * (w + 1) / workers);
+            pool.emplace_back([piece, w, &func, &range] {
+                bool skip_first = w == 0;// already done above
+                rangeFor_s(piece, [&](auto&& i) {
+                    if (skip_first) {
+                        skip_first = false;
+                        return;
+                    }
+                    func(i);
+                });
+            });
+        }
+        for (auto& t : pool) t.join();
+        return std::forward<F>(func);
     }
     template <std::size_t d, typename ReOp, typename F>
     auto rangeReduce_s(const DS::Range<d>& range, ReOp&& op, F&& func) {

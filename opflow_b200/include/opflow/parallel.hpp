@@ -183,7 +183,10 @@ namespace OpFlow {
     inline auto& getGlobalParallelInfo() { return internal::GLOBAL_PARALLELINFO; }
     inline ParallelPlan& getGlobalParallelPlan() { return internal::GLOBAL_PARALLELPLAN; }
     inline void setGlobalParallelInfo(const ParallelInfo& info) { internal::GLOBAL_PARALLELINFO = info; }
-    inline void setGlobalParallelPlan(const ParallelPlan& plan) { internal::GLOBAL_PARALLELPLAN = plan; }
+    inline void setGlobalParallelPlan(const ParallelPlan& plan) {
+        internal::GLOBAL_PARALLELPLAN = plan;
+        internal::g_host_threads = plan.shared_memory_workers_count > 0 ? plan.shared_memory_workers_count : 1;// host rangeFor workers
+    }
 
     // EvenSplitStrategy<F>::getSplitMap (EvenSplitStrategy.hpp:57-192): the arithmetic lives in the engine (opf_split_even),
     // bit-exact against EvenSplitStrategyTest.cpp:28-134

@@ -78,6 +78,34 @@ int main() {
     const double hx = 1.0 / (n - 1), hy = 2.0 / (n - 1);
     CHECK(std::abs(w.evalAt(DS::MDIndex<2> {2, 3}) - ((2 + 0.5) * hx + 10.0 * (3 + 0.5) * hy)) < 1e-14);
 
+    // 7. rangeFor with shared-memory workers in the global plan (RangeFor.hpp:69-84: tbb::parallel_for): a host lambda writing one
+    //    field from another, every index exactly once; also with a host-side array as the target (RangeForTest.cpp:131-175)
+    {
+        auto big = MeshBuilder<Mesh>().newMesh(301, 201).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).build();
+        auto a = ExprBuilder<Field>().setName("a").setMesh(big).setLoc({LocOnMesh::Center, LocOnMesh::Center}).build();
+        auto b = a;
+        b.name = "b";
+        a.initBy([](auto&& x) { return std::sin(3 * x[0]) + x[1]; });
+        b = 0;
+        auto info = makeParallelInfo();
+        info.threadInfo.thread_count = 4;
+        setGlobalParallelInfo(info);
+        setGlobalParallelPlan(makeParallelPlan(getGlobalParallelInfo(), ParallelIdentifier::SharedMem));
+        std::vector<int> hits((std::size_t) a.assignableRange.count(), 0);
+        const int nx = a.assignableRange.end[0] - a.assignableRange.start[0];
+        rangeFor(a.assignableRange, [&](auto&& i) {
+            b[i] = 2.0 * a[i] + 1.0;
+            hits[(std::size_t) (i[0] - a.assignableRange.start[0]) + (std::size_t) nx * (i[1] - a.assignableRange.start[1])] += 1;
+        });
+        int wrong = 0;
+        rangeFor_s(a.assignableRange, [&](auto&& i) { wrong += b[i] != 2.0 * a[i] + 1.0; });
+        for (int h : hits) wrong += h != 1;
+        CHECK(wrong == 0);
+        info.threadInfo.thread_count = 1;
+        setGlobalParallelInfo(info);
+        setGlobalParallelPlan(makeParallelPlan(getGlobalParallelInfo(), ParallelIdentifier::SharedMem));
+    }
+
     std::printf(failures ? "FAILED %d\n" : "PASS\n", failures);
     return failures ? 1 : 0;
 }
