@@ -206,3 +206,33 @@ def test_slab_and_even_split_neighbours_on_cpu():
         assert len(u.neighbors()) == 3
         sizes = sorted((s[1][0] - s[0][0]) * (s[1][1] - s[0][1]) for _, s, _, _ in u.neighbors())
         assert sizes == [1, 16, 16]  # one corner cell, two 16-cell edges
+
+
+def test_flux_limiter_and_convolution_ranges_without_a_device():
+    """opf_expr_prepare on plan-only fields (no GPU): accessible / local / logical ranges and result location of the flux-limiter
+    interpolators and convolutions equal what the unmodified reference prepared (tests/golden/ref_ops.json; D1FluxLimiter.hpp:155-203,
+    Convolution.hpp:66-82); a flux limiter applied to a field at the wrong location is refused like the reference's OP_ASSERT"""
+    import ops_golden as G
+    l = capi.lib()
+    d = G.load()
+    cx, cy = G.coords(d["nx"], d["ny"])
+    mesh = host.MeshBuilder(2).newMesh(d["nx"], d["ny"]).setMeshOfDim(0, cx).setMeshOfDim(1, cy).build()
+
+    def plan(loc):
+        b = host.ExprBuilder().setMesh(mesh).setLoc(loc).setExt(2)
+        for ax in range(2):
+            b.setBC(ax, 0, host.BCType.Neum, 0.).setBC(ax, 1, host.BCType.Neum, 0.)
+        return b.build(plan_only=True)
+
+    for c in d["cases"]:
+        sig, leaves, _, _ = G.describe(c)
+        fields = [plan(loc) for loc, _ in leaves]
+        F = (C.c_void_p * len(fields))(*[f.h for f in fields])
+        for which, key in ((capi.R_ACCESSIBLE, "acc"), (capi.R_LOCAL, "local"), (capi.R_LOGICAL, "logical")):
+            r, loc = capi.Range(), (C.c_int * 3)()
+            capi.check(l.opf_expr_prepare(sig.encode(), F, len(fields), which, C.byref(r), loc))
+            assert [list(x) for x in r.tup(2)] == c[key] and list(loc)[:2] == c["loc"], (sig, key)
+    u, e = plan([0, 1]), plan([0, 1])  # e is Corner along x: Cen2Cor must refuse it
+    F = (C.c_void_p * 2)(u.h, e.h)
+    r, loc = capi.Range(), (C.c_int * 3)()
+    assert l.opf_expr_prepare(b"FlQuickC2N<0,F<0>,F<1>>", F, 2, capi.R_ACCESSIBLE, C.byref(r), loc) != 0
