@@ -282,6 +282,12 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
  * lambda captures them by reference and is re-evaluated on every solve() (HYPREEqnSolveHandler.hpp:190-209 -> generateAb). */
 int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_fields, const double* lhs_scalars, int n_lhs_scalars);
 int opf_solver_levels(opf_solver_t s); /* number of multigrid levels built (1 = no hierarchy) */
+/* CSRMatrixGenerator::generate (src/Core/Equation/CSRMatrixGenerator.hpp:55-138) for callers that want the assembled system (an
+ * algebraic solver, a dump): row pointers [rows + 1], ascending column indices and values [cap_nnz], right-hand side [rows], rows =
+ * assignable cells in x-fastest order; pin_last replaces the last row by the identity like the reference's CSR route.  The values are
+ * probed off the matrix-free operator; in OPF_MODE_STENCIL they are the reference's assembled coefficients bit for bit. */
+int opf_solver_export_csr(opf_solver_t s, const char* rhs_signature, const opf_field_t* rhs_fields, int n_rhs_fields, const double* rhs_scalars,
+                          int n_rhs_scalars, int pin_last, long long cap_nnz, int* ptr, int* col, double* val, double* rhs, long long* nnz_out);
 int opf_solver_destroy(opf_solver_t s);
 
 #ifdef __cplusplus

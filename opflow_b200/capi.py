@@ -136,6 +136,7 @@ SIGNATURES = {
     "opf_solver_solve": (C.c_int, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.POINTER(SolveState)]),
     "opf_solver_update": (C.c_int, [_V, C.POINTER(_V), C.c_int, _D, C.c_int]),
     "opf_solver_levels": (C.c_int, [_V]),
+    "opf_solver_export_csr": (C.c_int, [_V, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int, C.c_longlong, _I, _I, _D, _D, C.POINTER(C.c_longlong)]),
     "opf_solver_destroy": (C.c_int, [_V]),
     "opf_reduce": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, _R, _D]),
     "opf_split_even": (C.c_int, [C.c_int, _R, C.c_int, _R]),

@@ -1264,6 +1264,133 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
 static void drop_graphs(opf_solver_s* s);
 int opf_solver_levels(opf_solver_t s) { return s ? (int) s->lv.size() : -1; }
 
+
+// CSRMatrixGenerator::generate (src/Core/Equation/CSRMatrixGenerator.hpp:55-138) for the matrix-free operator: rows and columns are
+// the ranks of the target's assignable cells in x-fastest order (DS::MDRangeMapper), columns ascending inside a row, b = rhs - lhs(0 with
+// the real boundary data) as the right-hand side, the LAST row replaced by the identity when pin_last is set (the CSR route pins the last
+// row, :78,84-91).  The coefficients are read off the operator by coloured probing (the lattice of build_diag): one operator
+// application per colour, each row picks the one column of that colour inside its footprint.  In STENCIL arithmetic the values are the
+// reference's assembled ones bit for bit (tests/test_gpu_coefficients.py).  Single rank only.
+int opf_solver_export_csr(opf_solver_t s, const char* rhs_signature, const opf_field_t* rhs_fields, int n_rhs_fields, const double* rhs_scalars,
+                          int n_rhs_scalars, int pin_last, long long cap_nnz, int* ptr, int* col, double* val, double* rhs, long long* nnz_out) {
+    if (!s || !ptr || !col || !val || !rhs || !rhs_signature) return fail(OPF_ERR_INVALID, "null argument");
+    opf_field_s* t = s->target;
+    if (t->n_ranks > 1) return fail(OPF_ERR_UNSUPPORTED, "opf_solver_export_csr: decomposed targets are not supported");
+    const int dim = t->dim;
+    const Range w = common(t->assignable, t->local);
+    const long long nrows = w.count();
+    if (nrows <= 0) return fail(OPF_ERR_INVALID, "empty assignable range");
+    std::vector<std::array<int, 3>> taps;
+    if (signature_unknown_taps(s->lhs_sig.c_str(), s->mask, taps) || taps.empty()) return fail(OPF_ERR_INVALID, "cannot derive the footprint of '%s'", s->lhs_sig.c_str());
+    // colouring: any (a, b, c, M) separating the footprint differences; small problems simply use one colour per cell offset pattern
+    std::vector<std::array<int, 3>> diff;
+    for (const auto& p1 : taps)
+        for (const auto& p2 : taps)
+            if (p1 != p2) diff.push_back({p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]});
+    long long per[3] = {0, 0, 0};
+    int n[3] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) {
+        n[d] = w.end[d] - w.start[d];
+        if (t->bc[d][0].type == OPF_BC_PERIODIC) per[d] = t->accessible.end[d] - t->accessible.start[d];
+    }
+    int lat[4] = {0, 0, 0, 0};
+    for (int M = (int) taps.size(); M <= 512 && !lat[3]; ++M)
+        for (int a = 1; a < std::min(std::max(2, M), 17) && !lat[3]; ++a)
+            for (int b = (dim >= 2 ? 1 : 0); b < (dim >= 2 ? M : 1) && !lat[3]; ++b)
+                for (int c = (dim >= 3 ? 1 : 0); c < (dim >= 3 ? M : 1) && !lat[3]; ++c) {
+                    if ((a * per[0]) % M || (b * per[1]) % M || (c * per[2]) % M) continue;
+                    bool ok = true;
+                    for (const auto& d : diff) {
+                        // periodic axes: differences are taken modulo the period, which the closing condition above makes harmless
+                        if ((((long long) a * d[0] + (long long) b * d[1] + (long long) c * d[2]) % M) == 0) {
+                            ok = false;
+                            break;
+                        }
+                    }
+                    if (ok) lat[0] = a, lat[1] = b, lat[2] = c, lat[3] = M;
+                }
+    if (!lat[3]) return fail(OPF_ERR_UNSUPPORTED, "opf_solver_export_csr: no probe colouring found for this footprint / periodic extents");
+    // b = rhs - lhs(0 with the real BC data), like opf_solver_solve
+    s->pin_active = false;
+    if (int rc = opf_assign_ex(s->B, OPF_OP_EQ, rhs_signature, rhs_fields, n_rhs_fields, rhs_scalars, n_rhs_scalars, OPF_ASSIGN_NO_PADDING)) return rc;
+    if (int rc = assign(s->E0, "S<0>", {}, {0.0})) return rc;
+    if (int rc = apply_lhs(s, s->E0, s->Q, 0, false, true)) return rc;
+    if (int rc = assign(s->B, "Sub<F<0>,F<1>>", {s->B, s->Q}, {})) return rc;
+    const opf_range wr = to_c(w);
+    std::vector<double> bvals((size_t) nrows), q((size_t) nrows);
+    if (int rc = opf_field_download(s->B, &wr, bvals.data())) return rc;
+    // affine constant part (lhs terms without the unknown) is removed from every probe
+    std::vector<double> c0((size_t) nrows, 0.0);
+    {
+        if (int rc = assign(s->Z, "S<0>", {}, {0.0})) return rc;
+        if (int rc = apply_lhs(s, s->Z, s->Q, 0, false, true)) return rc;
+        if (int rc = opf_field_download(s->Q, &wr, c0.data())) return rc;
+    }
+    auto rank_of = [&](const int g[3]) { return (long long) (g[0] - w.start[0]) + (long long) n[0] * ((g[1] - w.start[1]) + (long long) n[1] * (g[2] - w.start[2])); };
+    auto colour = [&](const int g[3]) {
+        long long v = ((long long) lat[0] * g[0] + (long long) lat[1] * g[1] + (long long) lat[2] * g[2]) % lat[3];
+        return (int) (v < 0 ? v + lat[3] : v);
+    };
+    std::vector<std::vector<std::pair<int, double>>> rows((size_t) nrows);
+    Mod3 mm{{1, 1, 1}, {lat[0], lat[1], lat[2], lat[3]}};
+    const BoxGrid bg = box_grid(w);
+    opf_field_s* X = s->lv[0].x;
+    for (int cidx = 0; cidx < lat[3]; ++cidx) {
+        color_fill_kernel<<<bg.grid, bg.block, 0, ctx().stream>>>(X->biased(X->cur), X->pitch1, X->pitch2, lr_of(w), dim, mm, cidx, 0, 0);
+        ctx().launches++;
+        if (int rc = apply_lhs(s, X, s->Q, 0, false, true)) return rc;
+        if (int rc = opf_field_download(s->Q, &wr, q.data())) return rc;
+        int g[3];
+        for (g[2] = w.start[2]; g[2] < w.end[2]; ++g[2])
+            for (g[1] = w.start[1]; g[1] < w.end[1]; ++g[1])
+                for (g[0] = w.start[0]; g[0] < w.end[0]; ++g[0]) {
+                    const long long r = rank_of(g);
+                    const double v = q[(size_t) r] - c0[(size_t) r];
+                    if (v == 0.0) continue;
+                    // the column: the footprint cell of this colour (folded back into the range: periodic wrap, BC mirror)
+                    int found = -1;
+                    for (const auto& o : taps) {
+                        int j[3] = {g[0] + o[0], g[1] + o[1], g[2] + o[2]};
+                        bool inside = true;
+                        for (int d = 0; d < dim; ++d) {
+                            if (per[d]) {
+                                while (j[d] < w.start[d]) j[d] += (int) per[d];
+                                while (j[d] >= w.end[d]) j[d] -= (int) per[d];
+                            } else if (j[d] < w.start[d] || j[d] >= w.end[d])
+                                inside = false;
+                        }
+                        if (inside && colour(j) == cidx) {
+                            found = (int) rank_of(j);
+                            break;
+                        }
+                    }
+                    if (found < 0) return fail(OPF_ERR_INVALID, "opf_solver_export_csr: probe response outside the footprint (row %lld, colour %d)", r, cidx);
+                    rows[(size_t) r].push_back({found, v});
+                }
+    }
+    if (int rc = assign(X, "S<0>", {}, {0.0})) return rc;
+    long long nnz = 0;
+    for (long long r = 0; r < nrows; ++r) {
+        auto& row = rows[(size_t) r];
+        if (pin_last && r == nrows - 1) {
+            row.assign(1, {(int) r, 1.0});
+            bvals[(size_t) r] = 0.0;
+        }
+        std::sort(row.begin(), row.end());
+        ptr[r] = (int) nnz;
+        for (const auto& e : row) {
+            if (nnz >= cap_nnz) return fail(OPF_ERR_INVALID, "opf_solver_export_csr: more than %lld non-zeros", cap_nnz);
+            col[nnz] = e.first;
+            val[nnz] = e.second;
+            ++nnz;
+        }
+        rhs[r] = bvals[(size_t) r];
+    }
+    ptr[nrows] = (int) nnz;
+    if (nnz_out) *nnz_out = nnz;
+    return OPF_OK;
+}
+
 int opf_solver_update(opf_solver_t s, const opf_field_t* lhs_fields, int n_lhs_fields, const double* lhs_scalars, int n_lhs_scalars) {
     if (!s) return fail(OPF_ERR_INVALID, "null solver");
     if (n_lhs_fields != (int) s->lhs_fields.size() || n_lhs_scalars != (int) s->lhs_scalars.size())

@@ -547,6 +547,26 @@ class EqnSolveHandler:
         check(lib().opf_solver_solve(self.h, sig.encode(), F, len(fields), S, len(scalars), C.byref(st)))
         return st
 
+    def export_csr(self, pin_last=False, cap_nnz=None):
+        """CSRMatrixGenerator::generate (CSRMatrixGenerator.hpp:55-138) -> (ptr, col, val, rhs) numpy arrays of the assembled system."""
+        import numpy as np
+        sig, fields, scalars = self._flatten(self.rhs)
+        F = (C.c_void_p * max(1, len(fields)))(*[f_.h for f_ in fields])
+        S = (C.c_double * max(1, len(scalars)))(*scalars)
+        rows = 1
+        for n in self.target.assignableRange.shape(self.target.dim):
+            rows *= n
+        cap = int(cap_nnz) if cap_nnz is not None else rows * 32
+        ptr = np.zeros(rows + 1, dtype=np.int32)
+        col = np.zeros(cap, dtype=np.int32)
+        val = np.zeros(cap, dtype=np.float64)
+        rhs = np.zeros(rows, dtype=np.float64)
+        nnz = C.c_longlong(0)
+        check(lib().opf_solver_export_csr(self.h, sig.encode(), F, len(fields), S, len(scalars), int(pin_last), cap,
+                                          ptr.ctypes.data_as(C.POINTER(C.c_int)), col.ctypes.data_as(C.POINTER(C.c_int)),
+                                          val.ctypes.data_as(C.POINTER(C.c_double)), rhs.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nnz)))
+        return ptr, col[:nnz.value].copy(), val[:nnz.value].copy(), rhs
+
     def __del__(self):
         try:
             lib().opf_solver_destroy(self.h)

@@ -137,3 +137,78 @@ def test_probed_operator_on_non_unit_spacing(engine, case):
             assert np.abs(A[rows] - G[rows]).max() <= 1e-12 * scale
             assert np.abs(rhs[rows] - grhs[rows]).max() <= 1e-12 * max(1.0, np.abs(grhs).max())
     host.set_mode(capi.MODE_FAST)
+
+
+def _csr_dense(ptr, col, val, n):
+    a = np.zeros((n, n))
+    for r in range(n):
+        for k in range(ptr[r], ptr[r + 1]):
+            a[r, col[k]] = val[k]
+    return a
+
+
+@pytest.mark.parametrize("bc", ["Dirc", "Neum", "Periodic"])
+def test_export_csr_equals_reference_generator(engine, bc):
+    """opf_solver_export_csr against the arrays the reference's own test asserts (CSRMatrixGeneratorTest.cpp:57-158): row pointers,
+    ascending column indices, values and right-hand side, last row pinned where the reference pins it.  The equation is written
+    exactly like the reference's, `1.0 == d2x(e) + d2y(e)` -> residual form lhs = 1 - L(e), rhs = 0."""
+    host.set_mode(capi.MODE_EXACT)
+    mesh = host.MeshBuilder(2).newMesh(5, 5).setMeshOfDim(0, 0., 4.).setMeshOfDim(1, 0., 4.).build()
+    b = host.ExprBuilder().setMesh(mesh).setName("p").setLoc([1, 1]).setExt(1)
+    for d in range(2):
+        for s in range(2):
+            if bc == "Periodic":
+                b.setBC(d, s, host.BCType.Periodic)
+            else:
+                b.setBC(d, s, host.BCType.Dirc if bc == "Dirc" else host.BCType.Neum, 0.)
+    p = b.build()
+    g = GOLD[bc]
+    h = host.EqnSolveHandler(lambda e: (1.0 - (d2x(D2, e) + d2y(D2, e)), 0.0), p, tol=1e-10, maxIter=10)
+    ptr, col, val, rhs = h.export_csr(pin_last=g["pinned_last"])
+    assert ptr.tolist() == g["ptr"]
+    assert col.tolist() == g["col"]
+    assert val.tolist() == [float(v) for v in g["val"]]
+    assert rhs.tolist() == [float(v) for v in g["rhs"]]
+    host.set_mode(capi.MODE_FAST)
+
+
+@pytest.mark.parametrize("case", _ref_csr_cases(), ids=lambda c: f"{'stretched' if c['stretched'] else 'uniform'}-{'center' if c['loc'] else 'corner'}-bc{c['bc']}")
+def test_export_csr_non_unit_spacing_bit_exact(engine, case):
+    """Exported CSR in STENCIL mode == the matrix assembled by the unmodified reference on non-unit / stretched spacing
+    (tests/golden/ref_csr.json): every stored value and the right-hand side bit for bit; the reference may additionally store explicit
+    zeros (a coefficient that cancelled), which a probe cannot see, so the pattern is compared as exported <= reference."""
+    c = case
+    nx, ny = c["dims"]
+    mb = host.MeshBuilder(2).newMesh(nx, ny)
+    if c["stretched"]:
+        mb.setMeshOfDim(0, _stretched(nx, 0.7)).setMeshOfDim(1, _stretched(ny, 1.3))
+    else:
+        mb.setMeshOfDim(0, 0., 0.7).setMeshOfDim(1, 0., 1.3)
+    mesh = mb.build()
+    b = host.ExprBuilder().setMesh(mesh).setName("p").setLoc([c["loc"]] * 2).setExt(1)
+    for d in range(2):
+        if c["bc"] == 0:
+            b.setBC(d, 0, host.BCType.Dirc, 0.25 * (d + 1)).setBC(d, 1, host.BCType.Dirc, -0.5)
+        elif c["bc"] == 1:
+            b.setBC(d, 0, host.BCType.Neum, 0.125).setBC(d, 1, host.BCType.Neum, 0.)
+        else:
+            b.setBC(d, 0, host.BCType.Periodic).setBC(d, 1, host.BCType.Periodic)
+    host.set_mode(capi.MODE_STENCIL)
+    p = b.build()
+    (s0, s1), (e0, e1) = c["range"]
+    N = (e0 - s0) * (e1 - s1)
+    # `1 == L(e)` moved to one side without an e-free term on the left, so no constant is subtracted from the probes: -L(e) == -1
+    h = host.EqnSolveHandler(lambda e: (-(d2x(D2, e) + d2y(D2, e)), -1.0), p, tol=1e-10, maxIter=10)
+    ptr, col, val, rhs = h.export_csr(pin_last=c["pinned_last"])
+    gval = [float.fromhex(v) for v in c["val"]]
+    grhs = np.array([float.fromhex(v) for v in c["rhs"]])
+    assert len(ptr) == N + 1
+    for r in range(N):
+        gold = {c["col"][k]: gval[k] for k in range(c["ptr"][r], c["ptr"][r + 1])}
+        mine = {int(col[k]): float(val[k]) for k in range(ptr[r], ptr[r + 1])}
+        assert list(mine) == sorted(mine), "columns not ascending"
+        assert set(mine) <= set(gold), (r, mine, gold)
+        for j, v in gold.items():
+            assert mine.get(j, 0.0) == v, (r, j, mine.get(j), v)
+    assert np.array_equal(rhs, grhs)
+    host.set_mode(capi.MODE_FAST)
