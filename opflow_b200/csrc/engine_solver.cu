@@ -356,6 +356,25 @@ namespace {
         const long long o = (long long) (r.lo[0] + x0) + (long long) (r.lo[1] + (int) blockIdx.y) * s1 + (long long) (r.lo[2] + (int) blockIdx.z) * s2;
         u[o] -= m;
     }
+    // coefficient field of a coarse level = its fine-level parent sampled at the coarse unknown positions: a Corner axis injects the
+    // coinciding node (coarse node i = fine node 2i), a Center axis averages the two fine cells under the coarse cell
+    struct CoefMap {
+        int f0[3], c0[3];// first mesh index of the fine / coarse level
+        int avg[3];      // 1: Center axis (two children), 0: Corner axis (injection) or unused axis
+    };
+    __global__ void __launch_bounds__(256) coef_restrict_kernel(const double* __restrict__ fine, long long fs1, long long fs2, double* __restrict__ coarse,
+                                                                long long cs1, long long cs2, opf::LaunchRange r, CoefMap m) {
+        const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x0 >= r.hi[0] - r.lo[0]) return;
+        const int i = r.lo[0] + x0, j = r.lo[1] + (int) blockIdx.y, k = r.lo[2] + (int) blockIdx.z;
+        const int fi = m.f0[0] + 2 * (i - m.c0[0]), fj = m.f0[1] + 2 * (j - m.c0[1]), fk = m.f0[2] + 2 * (k - m.c0[2]);
+        double acc = 0.0;
+        for (int c = 0; c <= m.avg[2]; ++c)
+            for (int b = 0; b <= m.avg[1]; ++b)
+                for (int a = 0; a <= m.avg[0]; ++a) acc += fine[(long long) (fi + a) + (long long) (fj + b) * fs1 + (long long) (fk + c) * fs2];
+        const int cnt = (1 + m.avg[0]) * (1 + m.avg[1]) * (1 + m.avg[2]);
+        coarse[(long long) i + (long long) j * cs1 + (long long) k * cs2] = acc / (double) cnt;
+    }
     __global__ void set_cell_kernel(double* u, long long off, double v) { u[off] = v; }
     __global__ void copy_cell_kernel(double* dst, const double* src, long long off) { dst[off] = src[off]; }
 
@@ -540,6 +559,10 @@ struct opf_solver_s {
         XferTab tab{};
         void* tab_mem = nullptr;
         bool tab_ready = false;
+        // coarse levels of an operator with coefficient fields: one restricted copy per non-unknown lhs leaf (same slot order as
+        // lhs_fields; empty on level 0, which reads the caller's fields), and the constant part of an affine lhs on this level
+        std::vector<opf_field_s*> coef;
+        opf_field_s* c0 = nullptr;
     };
     opf_field_s* target = nullptr;
     std::string lhs_sig, res_sig, smooth_sig;
@@ -587,6 +610,8 @@ struct opf_solver_s {
     bool pinned = false;
     long long pin_off = 0;
     bool setup_done = false, mg = false, has_res_sig = false;
+    bool coef_mg = false;   // the hierarchy carries restricted coefficient fields (lhs has leaves besides the unknown)
+    bool mg_bypass = false; // coefficient operator whose diagonal dominates (Jacobi is enough): the V-cycle stops at level 0
     bool singular = false;  // pinned AND the operator annihilates constants (all-Neumann / periodic)
     bool pin_active = false;// the Krylov-level operator currently carries the identity row of the pinned unknown
     double omega = 0.8;
@@ -622,15 +647,28 @@ namespace {
     }
     // q = lhs(in): ghost fill of `in` with its (homogeneous) BCs, then the expression functor
     // raw: the expression itself, constant part included (used once per solve to build b)
+    // which buffer of every caller-owned coefficient field is current (an aliased stencil assignment to such a field flips it):
+    // part of the key of every captured graph, whose launches carry the buffer addresses.  Bits 16.. ; the low 16 are the levels'.
+    unsigned coef_parity(const Solver* s) {
+        unsigned pp = 0;
+        for (size_t k = 0; k < s->lhs_fields.size() && k < 16; ++k)
+            if (!((s->mask >> k) & 1u) && s->lhs_fields[k]) pp |= (unsigned) (s->lhs_fields[k]->cur & 1) << (16 + k);
+        return pp;
+    }
+    // the coefficient leaf k of lhs as level `level` sees it
+    opf_field_s* leaf(Solver* s, int level, int k) { return (level > 0 && !s->lv[level].coef.empty()) ? s->lv[level].coef[k] : s->lhs_fields[k]; }
     int apply_lhs(Solver* s, opf_field_s* in, opf_field_s* out, int level, bool pin = true, bool raw = false) {
         if (int rc = field_update_padding(in)) return rc;
         opf_field_t F[OPF_MAX_FIELDS];
         const int nf = (int) s->lhs_fields.size();
-        for (int k = 0; k < nf; ++k) F[k] = ((s->mask >> k) & 1u) ? in : s->lhs_fields[k];
+        for (int k = 0; k < nf; ++k) F[k] = ((s->mask >> k) & 1u) ? in : leaf(s, level, k);
         if (int rc = opf_assign_ex(out, OPF_OP_EQ, s->lhs_sig.c_str(), F, nf, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING))
             return rc;
-        if (s->affine && level == 0 && !raw)
-            if (int rc = assign(out, "Sub<F<0>,F<1>>", {out, s->C0}, {})) return rc;
+        if (s->affine && !raw) {
+            opf_field_s* c0 = level == 0 ? s->C0 : s->lv[level].c0;
+            if (c0)
+                if (int rc = assign(out, "Sub<F<0>,F<1>>", {out, c0}, {})) return rc;
+        }
         if (s->pin_active && pin && s->lv[level].owns_pin) {// identity row for the pinned unknown (HYPREEqnSolveHandler.hpp:145-163)
             copy_cell_kernel<<<1, 1, 0, ctx().stream>>>(out->biased(out->cur), in->biased(in->cur), s->lv[level].pin_off);
             ctx().launches++;
@@ -644,7 +682,7 @@ namespace {
             opf_field_t F[OPF_MAX_FIELDS];
             const int nf = (int) s->lhs_fields.size();
             F[0] = b;
-            for (int k = 0; k < nf; ++k) F[k + 1] = ((s->mask >> k) & 1u) ? x : s->lhs_fields[k];
+            for (int k = 0; k < nf; ++k) F[k + 1] = ((s->mask >> k) & 1u) ? x : leaf(s, level, k);
             return opf_assign_ex(r, OPF_OP_EQ, s->res_sig.c_str(), F, nf + 1, s->lhs_scalars.data(), (int) s->lhs_scalars.size(), OPF_ASSIGN_NO_PADDING);
         }
         if (int rc = apply_lhs(s, x, scratch, level, pin)) return rc;
@@ -770,7 +808,7 @@ namespace {
                 double S[OPF_MAX_SCALARS];
                 const int nc = (int) s->smooth_coef_leaf.size(), ns = (int) s->lhs_scalars.size();
                 F[0] = L.x, F[1] = L.dinv, F[2] = L.b;
-                for (int k = 0; k < nc; ++k) F[k + 3] = s->lhs_fields[s->smooth_coef_leaf[k]];
+                for (int k = 0; k < nc; ++k) F[k + 3] = leaf(s, level, s->smooth_coef_leaf[k]);
                 S[0] = s->omega;
                 for (int k = 0; k < ns; ++k) S[k + 1] = s->lhs_scalars[k];
                 if (int rc = opf_assign_ex(L.x, OPF_OP_EQ, s->smooth_sig.c_str(), F, nc + 3, S, ns + 1, OPF_ASSIGN_NO_PADDING)) return rc;
@@ -879,6 +917,7 @@ namespace {
         if (s->singular && !top_is_mean_free && (level == 0 || project_coarse))
             if (int rc = project_mean(s, L.b, L.w, L.g, L.dist)) return rc;
         static const int coarse_sweeps = getenv("OPF_MG_COARSE_SWEEPS") ? atoi(getenv("OPF_MG_COARSE_SWEEPS")) : 8;
+        if (s->mg_bypass && level == 0) return smooth(s, 0, std::max(1, s->params.num_pre_relax), zero_guess);
         if (level == last) return smooth(s, level, last == 0 ? std::max(1, s->params.num_pre_relax) : coarse_sweeps, zero_guess);
         const int pre = std::max(1, s->params.num_pre_relax), post = std::max(1, s->params.num_post_relax);
         if (int rc = smooth(s, level, pre, zero_guess)) return rc;
@@ -952,7 +991,7 @@ namespace {
                 };
                 const int graphs_on = opf_internal_opt(OPF_OPT_GRAPHS);
                 if (!graphs_on || s->lv[0].dist || s->in_loop_capture) return body();// NCCL exchanges inside: not captured; inside the loop capture: inlined
-                unsigned parity = (unsigned) z->cur;
+                unsigned parity = (unsigned) z->cur | coef_parity(s);
                 for (size_t lv = 1; lv < s->lv.size(); ++lv) parity |= (unsigned) s->lv[lv].x->cur << lv;
                 Solver::VGraph* g = nullptr;
                 for (auto& e : s->vgraphs)
@@ -963,7 +1002,7 @@ namespace {
                 }
                 Context& c = ctx();
                 auto current_parity = [&]() {
-                    unsigned pp = (unsigned) z->cur;
+                    unsigned pp = (unsigned) z->cur | coef_parity(s);
                     for (size_t lv = 1; lv < s->lv.size(); ++lv) pp |= (unsigned) s->lv[lv].x->cur << lv;
                     return pp;
                 };
@@ -1041,6 +1080,35 @@ namespace {
         return opf_field_create(&d, name);
     }
 
+    void free_level_fields(Solver::Level& L);
+    // coarse copy of a coefficient field: same staggering and boundary conditions (real values: the lid speed stays the lid speed)
+    opf_field_s* make_coef_field(opf_field_s* like, opf_mesh_s* mesh, const char* name) {
+        opf_field_desc d{};
+        d.mesh = mesh;
+        for (int a = 0; a < like->dim; ++a) {
+            d.loc[a] = like->loc[a];
+            for (int sd = 0; sd < 2; ++sd) {
+                d.bc[a][sd].type = like->bc[a][sd].type;
+                d.bc[a][sd].value = like->bc[a][sd].value;
+                d.bc[a][sd].face = nullptr;
+                d.ext[a][sd] = like->ext[a][sd];
+            }
+        }
+        d.padding = like->padding;
+        d.n_ranks = 0;
+        return opf_field_create(&d, name);
+    }
+    // can the hierarchy carry this coefficient field?  same mesh as the unknown, one rank, constant boundary values
+    bool coef_coarsenable(const opf_field_s* f, const opf_field_s* t) {
+        if (!f || f->dim != t->dim || f->n_ranks > 1) return false;
+        for (int d = 0; d < t->dim; ++d) {
+            if (f->mesh->dims[d] != t->mesh->dims[d] || f->mesh->range.start[d] != t->mesh->range.start[d]) return false;
+            for (int sd = 0; sd < 2; ++sd)
+                if (f->bc[d][sd].face_dev) return false;
+        }
+        return true;
+    }
+
     int build_levels(Solver* s) {
         opf_field_s* t = s->target;
         const int dim = t->dim;
@@ -1071,7 +1139,15 @@ namespace {
         bool pure = true;
         for (size_t k = 0; k < s->lhs_fields.size(); ++k)
             if (!((s->mask >> k) & 1u)) pure = false;
-        s->mg = want_mg && pure && (t->n_ranks <= 1 || (comm_active() && !t->cell_split.empty()));
+        // ... or whose coefficient fields can be carried down the hierarchy (OPF_MG_COEF: 0 never -- such a request degrades to Jacobi
+        // as before --, 1 (default) when the level-0 diagonal does not dominate, 2 always)
+        static const int coef_opt = getenv("OPF_MG_COEF") ? atoi(getenv("OPF_MG_COEF")) : 1;
+        bool carry = !pure && coef_opt > 0 && t->n_ranks <= 1;
+        if (carry)
+            for (size_t k = 0; k < s->lhs_fields.size(); ++k)
+                if (!((s->mask >> k) & 1u) && !coef_coarsenable(s->lhs_fields[k], t)) carry = false;
+        s->coef_mg = want_mg && carry;
+        s->mg = want_mg && (pure || carry) && (t->n_ranks <= 1 || (comm_active() && !t->cell_split.empty()));
         if (!s->mg) return OPF_OK;
         // cell-centred blocks of the current distributed level (empty once the hierarchy continues replicated on every rank)
         std::vector<Range> blocks = t->n_ranks > 1 ? t->cell_split : std::vector<Range>();
@@ -1122,6 +1198,16 @@ namespace {
             C.q = make_level_field(t, cm, "mg.q", sp);
             C.dinv = make_level_field(t, cm, "mg.dinv", sp);
             if (!C.x || !C.b || !C.r || !C.q || !C.dinv) return OPF_ERR_CUDA;
+            if (s->coef_mg) {
+                C.coef.assign(s->lhs_fields.size(), nullptr);
+                for (size_t k = 0; k < s->lhs_fields.size(); ++k) {
+                    if ((s->mask >> k) & 1u) continue;
+                    for (size_t q = 0; q < k && !C.coef[k]; ++q)// the same field in two slots shares its coarse copy
+                        if (!((s->mask >> q) & 1u) && s->lhs_fields[q] == s->lhs_fields[k]) C.coef[k] = C.coef[q];
+                    if (!C.coef[k] && !(C.coef[k] = make_coef_field(s->lhs_fields[k], cm, "mg.coef"))) return OPF_ERR_CUDA;
+                }
+                if (!(C.c0 = make_level_field(t, cm, "mg.c0", sp))) return OPF_ERR_CUDA;
+            }
             opf_mesh_destroy(cm);// fields hold their own references
             C.w = common(C.x->assignable, C.x->local);
             C.g = C.x->assignable;
@@ -1129,7 +1215,7 @@ namespace {
             C.pin_off = (long long) C.x->assignable.start[0] + (long long) C.x->assignable.start[1] * C.x->pitch1
                         + (long long) C.x->assignable.start[2] * C.x->pitch2;
             if (C.g.count() <= 0) {
-                for (opf_field_s* f : {C.x, C.b, C.r, C.q, C.dinv}) opf_field_destroy(f);
+                free_level_fields(C);
                 break;
             }
             s->lv.push_back(C);
@@ -1146,8 +1232,52 @@ namespace {
         if (L.tab_mem) cudaFree(L.tab_mem);
         L.tab_mem = nullptr;
         L.tab_ready = false;
-        for (opf_field_s* f : {L.x, L.b, L.r, L.q, L.dinv})
+        for (opf_field_s* f : {L.x, L.b, L.r, L.q, L.dinv, L.c0})
             if (f) opf_field_destroy(f);
+        L.x = L.b = L.r = L.q = L.dinv = L.c0 = nullptr;
+        for (size_t k = 0; k < L.coef.size(); ++k) {
+            if (!L.coef[k]) continue;
+            opf_field_destroy(L.coef[k]);
+            for (size_t q = k + 1; q < L.coef.size(); ++q)
+                if (L.coef[q] == L.coef[k]) L.coef[q] = nullptr;
+            L.coef[k] = nullptr;
+        }
+    }
+
+    // refresh the coarse copies of the coefficient fields (level l from level l - 1), their ghosts, and the constant part of an
+    // affine lhs on every coarse level
+    int restrict_coefs(Solver* s) {
+        const int dim = s->target->dim;
+        for (int l = 1; l < (int) s->lv.size(); ++l) {
+            auto &F = s->lv[l - 1], &C = s->lv[l];
+            for (size_t k = 0; k < C.coef.size(); ++k) {
+                opf_field_s* dst = C.coef[k];
+                if (!dst) continue;
+                bool seen = false;
+                for (size_t q = 0; q < k; ++q) seen = seen || C.coef[q] == dst;
+                if (seen) continue;
+                const opf_field_s* src = leaf(s, l - 1, (int) k);
+                CoefMap m{};
+                for (int d = 0; d < 3; ++d) {
+                    m.f0[d] = d < dim ? F.mesh->range.start[d] : 0;
+                    m.c0[d] = d < dim ? C.mesh->range.start[d] : 0;
+                    m.avg[d] = d < dim && dst->loc[d] == OPF_LOC_CENTER ? 1 : 0;
+                }
+                const Range r = common(dst->assignable, dst->local);
+                if (r.count() > 0) {
+                    coef_restrict_kernel<<<box_grid(r).grid, box_grid(r).block, 0, ctx().stream>>>(src->biased(src->cur), src->pitch1, src->pitch2, dst->biased(dst->cur),
+                                                                                                 dst->pitch1, dst->pitch2, lr_of(r), m);
+                    ctx().launches++;
+                }
+                if (int rc = field_update_padding(dst)) return rc;
+            }
+            if (C.c0) {// lhs_l(0) with homogeneous boundary data
+                if (int rc = assign(C.x, "S<0>", {}, {0.0})) return rc;
+                if (int rc = apply_lhs(s, C.x, C.c0, l, false, true)) return rc;
+            }
+        }
+        OPF_CUDA(cudaGetLastError());
+        return OPF_OK;
     }
 }// namespace
 
@@ -1498,7 +1628,7 @@ static int pcg_body(opf_solver_s* s, const Range& w, cudaGraphConditionalHandle 
 }
 
 static unsigned loop_parity(opf_solver_s* s) {
-    unsigned pp = (unsigned) s->Z->cur;
+    unsigned pp = (unsigned) s->Z->cur | coef_parity(s);
     for (size_t lv = 1; lv < s->lv.size(); ++lv) pp |= (unsigned) s->lv[lv].x->cur << lv;
     return pp;
 }
@@ -1820,9 +1950,31 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
                               || s->params.type == OPF_SOLVER_SMG;
         const bool need_diag = s->mg || wants_mg || s->params.precond == OPF_SOLVER_JACOBI || s->params.type == OPF_SOLVER_JACOBI || s->pinned;
         if (need_diag)
-            for (int l = 0; l < (int) s->lv.size(); ++l)
-                if (l == 0 || s->mg)
-                    if (int rc = build_diag(s, l)) return rc;
+            if (int rc = build_diag(s, 0)) return rc;
+        if (s->coef_mg) {
+            // Is the hierarchy worth its cost?  For  a I + (convection) - b Laplacian  the row sum over the diagonal, r = |A.1| / |d|, is
+            // a / (a + 2 dim b / h^2): Jacobi-preconditioned Krylov sees a condition number of about (2 - r) / r.  r >= 1/4 everywhere
+            // (kappa <= 7, a handful of iterations) -> the V-cycle stops at its level-0 smoother, like round 1's behaviour, and the
+            // coarse levels are left alone.
+            static const int coef_opt = getenv("OPF_MG_COEF") ? atoi(getenv("OPF_MG_COEF")) : 1;
+            auto& L0 = s->lv[0];
+            double rmin = 0;
+            if (int rc = assign(L0.x, "S<0>", {}, {1.0})) return rc;
+            if (int rc = apply_lhs(s, L0.x, L0.q, 0, false)) return rc;
+            if (int rc = assign(L0.q, "Mul<F<0>,F<1>>", {L0.q, L0.dinv}, {})) return rc;
+            opf_field_t F[1] = {L0.q};
+            opf_range cr = to_c(w);
+            if (int rc = opf_reduce(OPF_RED_MIN, "Abs<F<0>>", F, 1, nullptr, 0, &cr, &rmin)) return rc;
+            if (int rc = assign(L0.x, "S<0>", {}, {0.0})) return rc;
+            const bool bypass = coef_opt < 2 && rmin >= 0.25;
+            if (bypass != s->mg_bypass) drop_graphs(s);// the captured V-cycle / loop bodies contain the other shape
+            s->mg_bypass = bypass;
+            if (!bypass)
+                if (int rc = restrict_coefs(s)) return rc;
+        }
+        if (need_diag && s->mg && !s->mg_bypass)
+            for (int l = 1; l < (int) s->lv.size(); ++l)
+                if (int rc = build_diag(s, l)) return rc;
         if (s->pinned) {
             // is the un-pinned operator singular with the constants as null space?  ||A.1||_inf vs ||diag||_inf
             auto& L0 = s->lv[0];
@@ -1860,7 +2012,7 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
     auto finish = [&](int rc_in) {
         if (rc_in) return rc_in;
         static const bool dbg = getenv("OPF_SOLVER_DEBUG") != nullptr;
-        if (dbg) fprintf(stderr, "[opf_solver] target=%s lhs=%s type=%d precond=%d mg=%d affine=%d pinned=%d singular=%d |b|=%.6e iters=%d rel=%.3e\n", t->name.c_str(), s->lhs_sig.substr(0, 40).c_str(), s->params.type, s->params.precond, (int) s->mg, (int) s->affine, (int) s->pinned, (int) s->singular, bnorm, iters, rel);
+        if (dbg) fprintf(stderr, "[opf_solver] target=%s lhs=%s type=%d precond=%d mg=%d coef_mg=%d bypass=%d levels=%d affine=%d pinned=%d singular=%d |b|=%.6e iters=%d rel=%.3e\n", t->name.c_str(), s->lhs_sig.substr(0, 40).c_str(), s->params.type, s->params.precond, (int) s->mg, (int) s->coef_mg, (int) s->mg_bypass, (int) s->lv.size(), (int) s->affine, (int) s->pinned, (int) s->singular, bnorm, iters, rel);
         if (state) {
             state->niter = iters;
             state->relerr = rel;

@@ -49,3 +49,9 @@ json.dump(out, open(root + "/tests/golden/liddriven2d_n65_s1000.json", "w"))
 PY
 rm -rf "$WORK"
 echo "examples.json and liddriven2d_n65_s1000.json written"
+
+# lid-driven cavity at sizes where the momentum operators need a multigrid preconditioner (nu dt / h^2 = 0.8 at 129^2 nodes, 3.3 at 257^2):
+# oracle/ref_drivers/ref_ld2d.cpp run by the unmodified reference, every 2nd / 4th value of u, v, p kept
+"$OUT/bin/ref_ld2d" --n 129 --steps 3 --threads 8 --tol 1e-10 --stride 2 --dump "$ROOT/tests/golden/ld2d_n129_s3" > /dev/null
+"$OUT/bin/ref_ld2d" --n 257 --steps 3 --threads 8 --tol 1e-10 --stride 4 --dump "$ROOT/tests/golden/ld2d_n257_s3" > /dev/null
+echo "ld2d_n129_s3_{u,v,p}.opfd and ld2d_n257_s3_{u,v,p}.opfd written"
