@@ -166,6 +166,11 @@ struct opf_field_s {
     double* buf[2] = {nullptr, nullptr};
     int cur = 0;
     long long pitch1 = 0, pitch2 = 0, lead = 0, elems = 0;
+    // Guard doubles allocated (and zeroed) before buf[i] and after buf[i] + elems.  The register-window skeleton stages the UNION of
+    // the rows / planes an operator may tap over all staggerings (the location is a run-time property, the tap set a compile-time
+    // one), up to 3 rows and 3 planes beyond the storage range; those values are never consumed, but the loads must land in mapped
+    // memory.  buf[i] itself is what every other piece of code sees (128-byte aligned).
+    long long guard = 0;
     std::vector<opfe::FillOp> fill0, fill1, fill2;// step 0, step 1, step 2 (single-rank periodic)
     // step 0 writes time-independent values (ConstDircBC / pre-evaluated FunctorDircBC) into Corner boundary nodes that no
     // assignment kernel ever touches (they lie outside assignableRange): once a buffer holds them they stay valid until

@@ -830,9 +830,26 @@ namespace opfe {
 
     int field_fill_periodic(opf_field_s* f) { return launch_fill_chain(f, {&f->fill2}, nullptr, nullptr); }
 
+    // device storage of a field buffer with its guard bands (engine.hpp: opf_field_s::guard)
+    cudaError_t field_buf_alloc(opf_field_s* f, int which) {
+        double* raw = nullptr;
+        const cudaError_t e = cudaMalloc(&raw, sizeof(double) * (f->elems + 2 * f->guard));
+        if (e != cudaSuccess) return e;
+        if (f->guard) {
+            cudaMemsetAsync(raw, 0, sizeof(double) * f->guard, ctx().stream);
+            cudaMemsetAsync(raw + f->guard + f->elems, 0, sizeof(double) * f->guard, ctx().stream);
+        }
+        f->buf[which] = raw + f->guard;
+        return cudaSuccess;
+    }
+    void field_buf_free(opf_field_s* f, int which) {
+        if (f->buf[which]) cudaFree(f->buf[which] - f->guard);
+        f->buf[which] = nullptr;
+    }
+
     int field_ensure_twin(opf_field_s* f) {
         if (f->buf[1 - f->cur]) return OPF_OK;
-        OPF_CUDA(cudaMalloc(&f->buf[1 - f->cur], sizeof(double) * f->elems));
+        OPF_CUDA(field_buf_alloc(f, 1 - f->cur));
         OPF_CUDA(cudaMemcpyAsync(f->buf[1 - f->cur], f->buf[f->cur], sizeof(double) * f->elems, cudaMemcpyDeviceToDevice, ctx().stream));
         f->bc0_clean[1 - f->cur] = f->bc0_clean[f->cur];
         return OPF_OK;
@@ -1006,6 +1023,7 @@ static opf_field_s* plan_field(const opf_field_desc* desc, const char* name, boo
     f->pitch1 = dim >= 2 ? ((f->lead + e0 + 15) / 16) * 16 : 0;
     f->pitch2 = dim >= 3 ? f->pitch1 * e1 : 0;
     f->elems = dim == 1 ? f->lead + e0 + 16 : (dim == 2 ? f->pitch1 * e1 : f->pitch2 * e2) + 16;
+    f->guard = dim == 1 ? 16 : ((3 * (f->pitch1 + f->pitch2) + 16 + 15) / 16) * 16;
     return f;
 }
 
@@ -1022,7 +1040,7 @@ opf_field_t opf_field_create(const opf_field_desc* desc, const char* name) {
     if (mesh_upload(desc->mesh)) return nullptr;
     opf_field_s* f = plan_field(desc, name, true);
     if (!f) return nullptr;
-    if (cudaMalloc(&f->buf[0], sizeof(double) * f->elems) != cudaSuccess) {
+    if (field_buf_alloc(f, 0) != cudaSuccess) {
         fail(OPF_ERR_CUDA, "cudaMalloc of %lld doubles failed for field '%s'", f->elems, f->name.c_str());
         cudaGetLastError();
         delete f;
@@ -1061,7 +1079,7 @@ opf_field_t opf_field_clone(opf_field_t src, const char* name) {
                 cudaMemcpy(bc.face_dev, bc.face.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
             }
         }
-    if (cudaMalloc(&f->buf[0], sizeof(double) * f->elems) != cudaSuccess) {
+    if (field_buf_alloc(f, 0) != cudaSuccess) {
         fail(OPF_ERR_CUDA, "cudaMalloc failed in clone");
         delete f;
         return nullptr;
@@ -1074,8 +1092,7 @@ opf_field_t opf_field_clone(opf_field_t src, const char* name) {
 int opf_field_destroy(opf_field_t f) {
     if (!f) return OPF_OK;
     if (ctx().inited) cudaStreamSynchronize(ctx().stream);
-    for (int i = 0; i < 2; ++i)
-        if (f->buf[i]) cudaFree(f->buf[i]);
+    for (int i = 0; i < 2; ++i) field_buf_free(f, i);
     if (f->halo_send) cudaFree(f->halo_send);
     if (f->halo_recv) cudaFree(f->halo_recv);
     for (int d = 0; d < D3; ++d)

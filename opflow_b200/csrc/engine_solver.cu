@@ -1423,15 +1423,28 @@ int opf_solver_export_csr(opf_solver_t s, const char* rhs_signature, const opf_f
         n[d] = w.end[d] - w.start[d];
         if (t->bc[d][0].type == OPF_BC_PERIODIC) per[d] = t->accessible.end[d] - t->accessible.start[d];
     }
+    // periodic axes: only cells of the range itself are coloured (ghosts are images), so two cells also meet across the seam -- their
+    // index difference is a footprint difference shifted by one period either way
+    for (int d = 0; d < dim; ++d) {
+        if (!per[d]) continue;
+        const size_t nd = diff.size();
+        for (size_t q = 0; q < nd; ++q)
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                auto e = diff[q];
+                e[d] += sgn * (int) per[d];
+                diff.push_back(e);
+            }
+    }
+    std::sort(diff.begin(), diff.end());
+    diff.erase(std::unique(diff.begin(), diff.end()), diff.end());
+    diff.erase(std::remove(diff.begin(), diff.end(), std::array<int, 3>{0, 0, 0}), diff.end());// a cell and itself
     int lat[4] = {0, 0, 0, 0};
     for (int M = (int) taps.size(); M <= 512 && !lat[3]; ++M)
         for (int a = 1; a < std::min(std::max(2, M), 17) && !lat[3]; ++a)
             for (int b = (dim >= 2 ? 1 : 0); b < (dim >= 2 ? M : 1) && !lat[3]; ++b)
                 for (int c = (dim >= 3 ? 1 : 0); c < (dim >= 3 ? M : 1) && !lat[3]; ++c) {
-                    if ((a * per[0]) % M || (b * per[1]) % M || (c * per[2]) % M) continue;
                     bool ok = true;
                     for (const auto& d : diff) {
-                        // periodic axes: differences are taken modulo the period, which the closing condition above makes harmless
                         if ((((long long) a * d[0] + (long long) b * d[1] + (long long) c * d[2]) % M) == 0) {
                             ok = false;
                             break;

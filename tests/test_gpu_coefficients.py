@@ -197,9 +197,15 @@ def test_export_csr_non_unit_spacing_bit_exact(engine, case):
     p = b.build()
     (s0, s1), (e0, e1) = c["range"]
     N = (e0 - s0) * (e1 - s1)
-    # `1 == L(e)` moved to one side without an e-free term on the left, so no constant is subtracted from the probes: -L(e) == -1
-    h = host.EqnSolveHandler(lambda e: (-(d2x(D2, e) + d2y(D2, e)), -1.0), p, tol=1e-10, maxIter=10)
+    # The reference assembles `1 == L(e)` as 1 - L(e): matrix -L, right-hand side -(1 - L(0)).  Exported here from  L(e) == 1  (no
+    # e-free term on the left, so no constant is subtracted from the probes): the same numbers with the opposite sign -- negation
+    # is exact --, except the pinned identity row, which is +1 / 0 on both sides.
+    h = host.EqnSolveHandler(lambda e: (d2x(D2, e) + d2y(D2, e), 1.0), p, tol=1e-10, maxIter=10)
     ptr, col, val, rhs = h.export_csr(pin_last=c["pinned_last"])
+    val, rhs = -val, -rhs
+    if c["pinned_last"]:
+        val[ptr[N - 1]:ptr[N]] *= -1.0
+        rhs[N - 1] *= -1.0
     gval = [float.fromhex(v) for v in c["val"]]
     grhs = np.array([float.fromhex(v) for v in c["rhs"]])
     assert len(ptr) == N + 1

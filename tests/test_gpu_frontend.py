@@ -284,5 +284,7 @@ def test_lid_driven_2d_at_multigrid_sizes_matches_reference(tmp_path, n, stride)
         scale = max(np.abs(ref).max(), 1e-3)
         err = np.abs(got - ref).max() / scale
         assert err <= 1e-8, f"{name}: relative L-inf difference {err:.3e}"
-    # the preconditioner did its work: a Jacobi-preconditioned GMRES needs tens of iterations per momentum solve at 256^2
-    assert info["momentum_iterations_per_step"] <= 30, info
+    # the preconditioner did its work: Jacobi-preconditioned GMRES needs ~50 iterations per momentum solve at 256^2 (OPF_MG_COEF=0:
+    # 99 per step), the V-cycle ~10.  At 128^2 the diagonal still dominates (row sum / diagonal = 0.38 >= 1/4) and the engine keeps Jacobi.
+    if n >= 257:
+        assert info["momentum_iterations_per_step"] <= 30, info
