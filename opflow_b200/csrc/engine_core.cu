@@ -369,7 +369,8 @@ namespace opfe {
         // single-spacing axis: every dx entry bitwise equal -> the reciprocal arrays are constant too (same formulas on the
         // same inputs; their unset end entries are never read by an in-range stencil)
         const auto& a = m->ax[d];
-        const bool uni = a.uniform;// decided once per axis in finish_axis (a 2^26-node axis must not be rescanned per launch)
+        static const int uniform_on = getenv("OPF_UNIFORM") ? atoi(getenv("OPF_UNIFORM")) : 1;// 0: A/B switch, every axis takes the array path
+        const bool uni = a.uniform && uniform_on;// decided once per axis in finish_axis (a 2^26-node axis must not be rescanned per launch)
         v.uniform = uni ? 1 : 0;
         if (uni) {
             const double h = a.dx[0];

@@ -446,14 +446,13 @@ namespace opf {
         static constexpr bool uni = false;
         const AxisView& ax;
         int q;
-        // a single-spacing axis (AxisView::uniform, warp-uniform flag) serves its coefficients from the kernel-parameter constant bank:
-        // the many-operand expressions that take this skeleton (semi-implicit momentum operators) otherwise issue ~100 coefficient
-        // loads per cell
+        // (serving a single-spacing axis from the kernel-parameter constant bank behind a warp-uniform `ax.uniform ? ... : ...` was tried
+        // here: the two-way code made fe_tg3d 35 % larger and its momentum operators 15 % slower -- profiles/r2_summary.md section 6)
         template <int O> __device__ __forceinline__ double x() const { return __ldg(ax.x + q + O); }
-        template <int O> __device__ __forceinline__ double dx() const { return ax.uniform ? ax.u[CF_DX] : __ldg(ax.dx + q + O); }
-        template <int O> __device__ __forceinline__ double rdx() const { return ax.uniform ? ax.u[CF_RDX] : __ldg(ax.rdx + q + O); }
-        template <int O> __device__ __forceinline__ double rdxh() const { return ax.uniform ? ax.u[CF_RDXH] : __ldg(ax.rdxh + q + O); }
-        template <int O> __device__ __forceinline__ double rdxc() const { return ax.uniform ? ax.u[CF_RDXC] : __ldg(ax.rdxc + q + O); }
+        template <int O> __device__ __forceinline__ double dx() const { return __ldg(ax.dx + q + O); }
+        template <int O> __device__ __forceinline__ double rdx() const { return __ldg(ax.rdx + q + O); }
+        template <int O> __device__ __forceinline__ double rdxh() const { return __ldg(ax.rdxh + q + O); }
+        template <int O> __device__ __forceinline__ double rdxc() const { return __ldg(ax.rdxc + q + O); }
     };
     template <class C, int D, int QO>
     struct WAcc {// register-cached coefficients of the window context (hoisted out of the march loop)
