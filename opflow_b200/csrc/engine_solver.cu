@@ -677,7 +677,13 @@ namespace {
     }
     // r = b - lhs(x)
     int residual(Solver* s, opf_field_s* x, opf_field_s* b, opf_field_s* r, opf_field_s* scratch, int level, bool pin = true) {
-        if (s->has_res_sig && !(s->pin_active && pin) && !s->affine) {
+        if (s->has_res_sig && !(s->pin_active && pin)) {
+            // affine lhs = A + c:  b - A x = (b + c) - lhs(x) -- the shifted right-hand side goes through the scratch field
+            opf_field_s* c0 = s->affine ? (level == 0 ? s->C0 : s->lv[level].c0) : nullptr;
+            if (c0) {
+                if (int rc = assign(scratch, "Add<F<0>,F<1>>", {b, c0}, {})) return rc;
+                b = scratch;
+            }
             if (int rc = field_update_padding(x)) return rc;
             opf_field_t F[OPF_MAX_FIELDS];
             const int nf = (int) s->lhs_fields.size();
