@@ -656,7 +656,8 @@ def run_c4(env, args, compact=False, n=4097):
     def lap(f):
         return d2x(D2, f) + d2y(D2, f)
     bf.assign(lap(pt))
-    h = EqnSolveHandler(lambda e: (lap(e), bf), p, type_=ST.PCG, precond=ST.PFMG, tol=1e-10, maxIter=100, pinValue=True, staticMat=True)
+    relax = int(os.environ.get("OPF_C4_RELAX", "1"))  # PFMG relaxType of the reference's LidDriven2D.cpp:48 is 1 (Jacobi); 2 = symmetric red-black GS
+    h = EqnSolveHandler(lambda e: (lap(e), bf), p, type_=ST.PCG, precond=ST.PFMG, tol=1e-10, maxIter=100, pinValue=True, staticMat=True, relaxType=relax)
     state = {}
 
     def solve():

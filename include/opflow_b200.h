@@ -254,8 +254,9 @@ typedef struct opf_solver_params { /* StructSolverParamsBase :39-51 + the per-so
     int static_mat, pin_value;
     double precond_tol;     /* PFMG-as-preconditioner tolerance (StructSolverPFMG.hpp:23-34); 0 = one V-cycle */
     int precond_max_iter;
-    int num_pre_relax, num_post_relax, relax_type; /* StructSolverPFMG.hpp:23-34 relaxType; every value runs weighted Jacobi
-                                                       (omega = 2d/(2d+1)): red-black Gauss-Seidel (2/3) is not built */
+    int num_pre_relax, num_post_relax, relax_type; /* StructSolverPFMG.hpp:23-34 relaxType.  0 / 1: weighted Jacobi (omega = 2d/(2d+1));
+                                                       2: symmetric red-black Gauss-Seidel (red-black before, black-red after the
+                                                       coarse correction); 3: red-black on both sides */
     int print_level;
     int k_dim;              /* GMRES restart length (StructSolverGMRES.hpp kDim; 0 = hypre's default 5) */
 } opf_solver_params;

@@ -26,6 +26,15 @@ OPF_BUILTIN(Sub<F<0>, Add<Add<D2C<0, F<1>>, D2C<1, F<2>>>, D2C<2, F<3>>>>)
 // fused weighted-Jacobi sweep x <- x + w*dinv*(b - L(x)) of the Poisson operator (engine_solver.cu smooth())
 OPF_BUILTIN(Add<F<0>, Mul<S<0>, Mul<F<1>, Sub<F<2>, Add<D2C<0, F<0>>, D2C<1, F<0>>>>>>>)
 OPF_BUILTIN(Add<F<0>, Mul<S<0>, Mul<F<1>, Sub<F<2>, Add<Add<D2C<0, F<0>>, D2C<1, F<0>>>, D2C<2, F<0>>>>>>>)
+// red-black Gauss-Seidel half-sweeps (PFMG relax_type 2 / 3): x = Par.dinv.b from a zero guess, x += Par.dinv.r from a residual, and
+// the fused form  x += Par.dinv.(b - L(x))  of the Poisson operator (engine_solver.cu smooth())
+OPF_BUILTIN(Mul<Par<0>, Mul<F<0>, F<1>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<0>, Mul<F<1>, F<2>>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<1>, Mul<F<1>, F<2>>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<0>, Mul<F<1>, Sub<F<2>, Add<D2C<0, F<0>>, D2C<1, F<0>>>>>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<1>, Mul<F<1>, Sub<F<2>, Add<D2C<0, F<0>>, D2C<1, F<0>>>>>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<0>, Mul<F<1>, Sub<F<2>, Add<Add<D2C<0, F<0>>, D2C<1, F<0>>>, D2C<2, F<0>>>>>>>)
+OPF_BUILTIN(Add<F<0>, Mul<Par<1>, Mul<F<1>, Sub<F<2>, Add<Add<D2C<0, F<0>>, D2C<1, F<0>>>, D2C<2, F<0>>>>>>>)
 // the equation of the reference's CSR generator test in residual form, `1.0 == d2x(e) + d2y(e)` -> 1 - L(e) (CSRMatrixGeneratorTest.cpp:57-158)
 OPF_BUILTIN(Sub<S<0>, Add<D2C<0, F<0>>, D2C<1, F<1>>>>)
 // 1-D Poisson / Helmholtz pieces

@@ -14,7 +14,7 @@
 namespace opfe {
 
     enum Kind {
-        K_F, K_S,
+        K_F, K_S, K_PAR,// K_PAR: cell-parity leaf Par<c> of the red-black smoother (engine_solver.cu); a scalar-like node
         K_ADD, K_SUB, K_MUL, K_DIV, K_MIN, K_MAX, K_POW, K_LT, K_LE, K_GT, K_GE, K_EQ, K_NE, K_AND, K_OR,
         K_NEG, K_POS, K_NOT, K_SQRT, K_ABS, K_EXP, K_LOG, K_SIN, K_COS, K_TAN, K_TANH, K_POW2,
         K_COND, K_UNI, K_BIN, K_FLC2N, K_FLN2C, K_CONV,// K_UNI / K_BIN: point-wise math functors without any special preparation (AMDS.hpp:40-89)
@@ -26,7 +26,7 @@ namespace opfe {
         bool has_axis;
     };
     static const KindInfo kinds[] = {
-            {"F", K_F, 0, false},         {"S", K_S, 0, false},         {"Add", K_ADD, 2, false},     {"Sub", K_SUB, 2, false},
+            {"F", K_F, 0, false},         {"S", K_S, 0, false},         {"Par", K_PAR, 0, false},         {"Add", K_ADD, 2, false},     {"Sub", K_SUB, 2, false},
             {"Mul", K_MUL, 2, false},     {"Div", K_DIV, 2, false},     {"Min", K_MIN, 2, false},     {"Max", K_MAX, 2, false},
             {"Pow", K_POW, 2, false},     {"Lt", K_LT, 2, false},       {"Le", K_LE, 2, false},       {"Gt", K_GT, 2, false},
             {"Ge", K_GE, 2, false},       {"Eq", K_EQ, 2, false},       {"Ne", K_NE, 2, false},       {"And", K_AND, 2, false},
@@ -97,16 +97,16 @@ namespace opfe {
             t.nodes.emplace_back();
             t.nodes[me].kind = ki->kind;
             t.nodes[me].nchild = ki->nchild;
-            if (ki->kind == K_F || ki->kind == K_S) {
+            if (ki->kind == K_F || ki->kind == K_S || ki->kind == K_PAR) {
                 int v;
                 if (!parse_int(v) || v < 0) {
                     err = "bad leaf index";
                     return -1;
                 }
                 t.nodes[me].leaf = v;
-                t.nodes[me].scalar = ki->kind == K_S;
+                t.nodes[me].scalar = ki->kind != K_F;
                 if (ki->kind == K_F) t.nfields = std::max(t.nfields, v + 1);
-                else
+                else if (ki->kind == K_S)
                     t.nscalars = std::max(t.nscalars, v + 1);
             } else {
                 if (name == "Adapt1" || name == "Adapt2") {// the functor's name is part of the signature (registry key), not of the tree
@@ -211,7 +211,8 @@ namespace opfe {
                 n.src = f;
                 break;
             }
-            case K_S: n.scalar = true; break;
+            case K_S:
+            case K_PAR: n.scalar = true; break;
             case K_COND: {
                 // CondOp::prepare (Conditional.hpp:45-70): props from arg2, ranges = common of the three
                 Node &c0 = ch(0), &c1 = ch(1), &c2 = ch(2);
@@ -417,7 +418,7 @@ namespace opfe {
             if ((mask >> n.leaf) & 1u) out.insert(out.end(), at.begin(), at.end());
             return;
         }
-        if (n.kind == K_S) return;
+        if (n.kind == K_S || n.kind == K_PAR) return;
         auto shifted = [&](int axis, int lo, int hi) {
             std::vector<std::array<int, 3>> r;
             for (const auto& o : at)

@@ -565,8 +565,8 @@ struct opf_solver_s {
         opf_field_s* c0 = nullptr;
     };
     opf_field_s* target = nullptr;
-    std::string lhs_sig, res_sig, smooth_sig;
-    bool has_smooth_sig = false;
+    std::string lhs_sig, res_sig, smooth_sig, rb_sig[2];
+    bool has_smooth_sig = false, has_rb_sig = false;
     std::vector<int> smooth_coef_leaf;
     std::vector<opf_field_s*> lhs_fields;
     std::vector<double> lhs_scalars;
@@ -802,8 +802,40 @@ namespace {
         return assign(L.x, "S<0>", {}, {0.0});
     }
 
-    int smooth(Solver* s, int level, int sweeps, bool zero_guess) {
+    // relax_type 0 / 1: (weighted) Jacobi.  2 / 3: red-black Gauss-Seidel (StructSolverPFMG.hpp:23-34) -- two half-sweeps with the exact
+    // diagonal on the cells of one (i + j + k) parity each; 2 is the symmetric variant (red-black before, black-red after the coarse
+    // correction, which keeps the V-cycle a symmetric preconditioner for PCG), 3 runs red-black on both sides.
+    int smooth(Solver* s, int level, int sweeps, bool zero_guess, bool post = false) {
         auto& L = s->lv[level];
+        const int rt = s->params.relax_type;
+        if (rt == 2 || rt == 3) {
+            const int first = (post && rt == 2) ? 1 : 0;
+            for (int it = 0; it < sweeps; ++it)
+                for (int h = 0; h < 2; ++h) {
+                    const int c = h == 0 ? first : 1 - first;
+                    if (it == 0 && h == 0 && zero_guess && c == 0) {// x = 0: the red cells get dinv * b, the black ones stay 0
+                        if (int rc = assign(L.x, "Mul<Par<0>,Mul<F<0>,F<1>>>", {L.dinv, L.b}, {})) return rc;
+                        continue;
+                    }
+                    if (it == 0 && h == 0 && zero_guess)
+                        if (int rc = assign(L.x, "S<0>", {}, {0.0})) return rc;
+                    if (s->has_rb_sig && !s->affine) {
+                        if (int rc = field_update_padding(L.x)) return rc;
+                        opf_field_t F[OPF_MAX_FIELDS];
+                        double S[OPF_MAX_SCALARS];
+                        const int nc = (int) s->smooth_coef_leaf.size(), ns = (int) s->lhs_scalars.size();
+                        F[0] = L.x, F[1] = L.dinv, F[2] = L.b;
+                        for (int k = 0; k < nc; ++k) F[k + 3] = leaf(s, level, s->smooth_coef_leaf[k]);
+                        S[0] = 1.0;
+                        for (int k = 0; k < ns; ++k) S[k + 1] = s->lhs_scalars[k];
+                        if (int rc = opf_assign_ex(L.x, OPF_OP_EQ, s->rb_sig[c].c_str(), F, nc + 3, S, ns + 1, OPF_ASSIGN_NO_PADDING)) return rc;
+                    } else {
+                        if (int rc = residual(s, L.x, L.b, L.r, L.q, level, false)) return rc;
+                        if (int rc = assign(L.x, c == 0 ? "Add<F<0>,Mul<Par<0>,Mul<F<1>,F<2>>>>" : "Add<F<0>,Mul<Par<1>,Mul<F<1>,F<2>>>>", {L.x, L.dinv, L.r}, {})) return rc;
+                    }
+                }
+            return OPF_OK;
+        }
         for (int it = 0; it < sweeps; ++it) {
             if (it == 0 && zero_guess) {
                 if (int rc = assign(L.x, "Mul<S<0>,Mul<F<0>,F<1>>>", {L.dinv, L.b}, {s->omega})) return rc;
@@ -974,7 +1006,7 @@ namespace {
             prolong_kernel<<<box_grid(L.w).grid, box_grid(L.w).block, 0, ctx().stream>>>(p);
         ctx().launches++;
         OPF_CUDA(cudaGetLastError());
-        return smooth(s, level, post, false);
+        return smooth(s, level, post, false, true);
     }
 
     int project_mean(Solver* s, opf_field_s* f, const Range& w, const Range& g, bool dist);
@@ -1366,6 +1398,10 @@ opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, co
         const int fused_on = opf_internal_opt(OPF_OPT_MG_FUSED);
         s->has_smooth_sig = fused_on && (int) coef_leaf.size() + 3 <= OPF_MAX_FIELDS && n_lhs_scalars + 1 <= OPF_MAX_SCALARS
                             && opf_expr_is_registered(s->smooth_sig.c_str()) != 0;
+        // fused red-black half-sweep  x <- x + Par<c> * dinv * (b - lhs(x)): same leaf numbering, the colour mask in place of w
+        for (int c = 0; c < 2; ++c) s->rb_sig[c] = "Add<F<0>,Mul<Par<" + std::to_string(c) + ">,Mul<F<1>,Sub<F<2>," + sm + ">>>>";
+        s->has_rb_sig = fused_on && (int) coef_leaf.size() + 3 <= OPF_MAX_FIELDS && n_lhs_scalars + 1 <= OPF_MAX_SCALARS
+                        && opf_expr_is_registered(s->rb_sig[0].c_str()) != 0 && opf_expr_is_registered(s->rb_sig[1].c_str()) != 0;
     }
     const Range w = common(target->assignable, target->local);
     s->pinned = params->pin_value != 0;

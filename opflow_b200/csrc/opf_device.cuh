@@ -224,6 +224,23 @@ namespace opf {
         static constexpr void taps(TS&, const TapGrid&) {}
     };
 
+    // Par<C>: 1.0 on the cells whose global index sum i + j + k has parity C, else 0.0 -- the colour mask of the red-black
+    // Gauss-Seidel half-sweeps (HYPRE PFMG relax_type 2 / 3, StructSolverPFMG.hpp:23-34).  Carries no ranges, like a scalar.
+    template <int C>
+    struct Par {
+        static constexpr int size = 1, maxaxis = -1, nf = 0;
+        template <int B, class P, bool A0>
+        __device__ __forceinline__ static double eval(const ExprArgs&, int i, int j, int k) {
+            return ((i + j + k) & 1) == C ? 1.0 : 0.0;
+        }
+        template <int B, class P, bool A0, int DI, int DJ, int DK, class Cx>
+        __device__ __forceinline__ static double ev(const Cx& c) {
+            return ((c.i0 + DI + c.j + DJ + c.k + DK) & 1) == C ? 1.0 : 0.0;
+        }
+        template <bool A0, class TS>
+        static constexpr void taps(TS&, const TapGrid&) {}
+    };
+
     // ------------------------------------------------------------------------------------------- point-wise
     // BinOpDefMacros.hpp.in:15-17 (operand order preserved), AMDS.hpp:34-91, MinMax.hpp:51-52, Compare.hpp, Boolean.hpp
 #define OPF_BINOP(Name, EXPR)                                                                                          \

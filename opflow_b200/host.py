@@ -500,13 +500,13 @@ class EqnSolveHandler:
     f(e) must return (lhs, rhs) -- the two sides of the reference's `lhs == rhs`; lhs linear in e, rhs independent of e."""
 
     def __init__(self, f, target: Field, type_=StructSolverType.PCG, precond=StructSolverType.NONE, tol=1e-10, maxIter=100,
-                 staticMat=False, pinValue=False, numPreRelax=1, numPostRelax=1, precondMaxIter=1):
+                 staticMat=False, pinValue=False, numPreRelax=1, numPostRelax=1, precondMaxIter=1, relaxType=1):
         e = Unknown()
         self.target, self.e = target, e
         self.lhs, self.rhs = f(e)
         p = capi.SolverParams(type=type_, precond=precond, tol=tol, max_iter=maxIter, static_mat=int(staticMat), pin_value=int(pinValue),
                               precond_tol=0.0, precond_max_iter=precondMaxIter, num_pre_relax=numPreRelax, num_post_relax=numPostRelax,
-                              relax_type=1, print_level=0)
+                              relax_type=relaxType, print_level=0)
         sig, fields, scalars = self._flatten(self.lhs)
         mask = 0
         for k, f_ in enumerate(fields):

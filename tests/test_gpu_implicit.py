@@ -77,3 +77,53 @@ def test_multigrid_is_mesh_independent(engine):
         st2 = h.solve()
         assert st2.niter <= 1
     assert max(iters) <= 2 * min(iters) + 4, iters
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("relax", [2, 3])
+def test_red_black_gauss_seidel_smoother(engine, case, relax):
+    """PFMG relaxType 2 / 3 (StructSolverPFMG.hpp:23-34: symmetric and plain red-black Gauss-Seidel) as the V-cycle smoother: the
+    solution is the reference's (HYPRE solve, 1e-10 relative) whatever the smoother; the symmetric variant keeps PCG applicable,
+    the plain one runs under GMRES.  The stronger smoother must not need more iterations than weighted Jacobi."""
+    host.set_mode(capi.MODE_EXACT)
+    dim = len(case["n"])
+    rng = capi.Range.make(case["range"][0], case["range"][1])
+    shape = rng.shape(dim)
+    ref = np.array(case["p"]).reshape(shape, order="F")
+    iters = {}
+    for rt in (1, relax):
+        p, bf = build(case, "p"), build(case, "b")
+        bf.from_numpy(np.array(case["b"]).reshape(shape, order="F"), rng)
+        p.assign(0.0)
+        h = EqnSolveHandler(lambda e: (lap(e, dim), bf), p, type_=ST.PCG if rt != 3 else ST.GMRES, precond=ST.PFMG, tol=1e-13, maxIter=200,
+                            pinValue=bool(case["pin"]), relaxType=rt)
+        st = h.solve()
+        iters[rt] = st.niter
+        err = np.abs(p.to_numpy(rng) - ref).max() / np.abs(ref).max()
+        assert err <= 1e-10, f"{case['name']} relaxType {rt}: solution differs from the reference by {err:.3e} (niter={st.niter}, relres={st.relerr:.2e})"
+    if relax == 2:
+        assert iters[2] <= iters[1], iters
+
+
+def test_red_black_smoother_at_c4_shape(engine):
+    """4-level-deep hierarchy, all-Neumann pinned Poisson problem of LidDriven2D (BASELINE C4's operator) at 1024^2 cells in FAST mode:
+    iteration counts of V(1,1) cycles with weighted Jacobi and with symmetric red-black Gauss-Seidel, same solution"""
+    host.set_mode(capi.MODE_FAST)
+    n = 1025
+    c = {"n": [n, n], "lo": [0, 0], "hi": [1, 1], "loc": [1, 1], "bc": "Neum", "bcv": 0.0, "ext": 1}
+    xs = (np.arange(n - 1) + 0.5) / (n - 1)
+    exact = np.asfortranarray(np.cos(np.pi * xs)[:, None] * np.cos(2 * np.pi * xs)[None, :])
+    sols, iters = {}, {}
+    for rt in (1, 2):
+        p, bf, pt = build(c, "p"), build(c, "b"), build(c, "pt")
+        pt.from_numpy(exact)
+        bf.assign(lap(pt, 2))
+        p.assign(0.0)
+        h = EqnSolveHandler(lambda e: (lap(e, 2), bf), p, type_=ST.PCG, precond=ST.PFMG, tol=1e-10, maxIter=100, pinValue=True, staticMat=True, relaxType=rt)
+        st = h.solve()
+        assert st.relerr <= 1e-10
+        sols[rt], iters[rt] = p.to_numpy(), st.niter
+    d = sols[1] - sols[2]
+    assert np.abs(d - d.mean()).max() <= 1e-8 * np.abs(sols[1]).max()
+    assert iters[2] <= iters[1], iters
+    print("iterations: Jacobi", iters[1], "red-black GS", iters[2])
