@@ -4,7 +4,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 if [ "$2" = "tests" ]; then python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r2_gputests_${N}gpu.txt; cat gpurun_out/r2_gputests_${N}gpu.txt; fi
-for rep in a b; do
+for rep in ${OPF_SCALE_REPS:-a b}; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_scale_n${N}${rep}.out 2> gpurun_out/r2_scale_n${N}${rep}.err
 grep '^{"metric' gpurun_out/r2_scale_n${N}${rep}.out > gpurun_out/r2_scale_n${N}${rep}.json; python - <<PY
 import json
