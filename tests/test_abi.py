@@ -236,3 +236,27 @@ def test_flux_limiter_and_convolution_ranges_without_a_device():
     F = (C.c_void_p * 2)(u.h, e.h)
     r, loc = capi.Range(), (C.c_int * 3)()
     assert l.opf_expr_prepare(b"FlQuickC2N<0,F<0>,F<1>>", F, 2, capi.R_ACCESSIBLE, C.byref(r), loc) != 0
+
+
+def test_parity_leaf_of_the_red_black_smoother_without_a_device():
+    """Par<c> (the colour mask of the red-black Gauss-Seidel half-sweeps, PFMG relaxType 2 / 3) is a scalar-like leaf: it is part of
+    the grammar, its half-sweep kernels are compiled in for the Poisson operators, and it neither adds ranges nor field / scalar slots"""
+    l = capi.lib()
+    for sig in ("Mul<Par<0>,Mul<F<0>,F<1>>>", "Add<F<0>,Mul<Par<1>,Mul<F<1>,F<2>>>>",
+                "Add<F<0>,Mul<Par<0>,Mul<F<1>,Sub<F<2>,Add<D2C<0,F<0>>,D2C<1,F<0>>>>>>>",
+                "Add<F<0>,Mul<Par<1>,Mul<F<1>,Sub<F<2>,Add<Add<D2C<0,F<0>>,D2C<1,F<0>>>,D2C<2,F<0>>>>>>>"):
+        assert l.opf_expr_is_registered(sig.encode()), sig
+    mesh = host.MeshBuilder(2).newMesh(9, 7).setMeshOfDim(0, 0., 1.).setMeshOfDim(1, 0., 1.).build()
+    b = host.ExprBuilder().setMesh(mesh).setLoc([1, 1]).setExt(1)
+    for ax in range(2):
+        b.setBC(ax, 0, host.BCType.Neum, 0.).setBC(ax, 1, host.BCType.Neum, 0.)
+    x, dinv, rhs = (b.build(plan_only=True) for _ in range(3))
+    F = (C.c_void_p * 3)(x.h, dinv.h, rhs.h)
+    got = {}
+    for sig in (b"Add<F<0>,Mul<Par<1>,Mul<F<1>,F<2>>>>", b"Add<F<0>,Mul<S<0>,Mul<F<1>,F<2>>>>"):
+        r, loc = capi.Range(), (C.c_int * 3)()
+        capi.check(l.opf_expr_prepare(sig, F, 3, capi.R_ACCESSIBLE, C.byref(r), loc))
+        got[sig] = (r.tup(2), list(loc)[:2])
+    assert got[b"Add<F<0>,Mul<Par<1>,Mul<F<1>,F<2>>>>"] == got[b"Add<F<0>,Mul<S<0>,Mul<F<1>,F<2>>>>"]
+    r, loc = capi.Range(), (C.c_int * 3)()
+    assert l.opf_expr_prepare(b"Par<x>", F, 0, capi.R_ACCESSIBLE, C.byref(r), loc) != 0

@@ -127,3 +127,37 @@ def test_red_black_smoother_at_c4_shape(engine):
     assert np.abs(d - d.mean()).max() <= 1e-8 * np.abs(sols[1]).max()
     assert iters[2] <= iters[1], iters
     print("iterations: Jacobi", iters[1], "red-black GS", iters[2])
+
+
+@pytest.mark.parametrize("shape,loc", [((70, 37), [1, 1]), ((41, 23), [0, 0]), ((130, 21, 19), [1, 1, 1]), ((71, 17, 13), [0, 1, 0])])
+def test_parity_leaf_masks_by_global_index(engine, shape, loc):
+    """Par<c> is 1 where (i + j + k) of the GLOBAL cell index has parity c -- also for Corner-Dirichlet fields whose assignable range starts
+    at 1, in the register-window skeleton (2-D, small 3-D) and the TMA skeleton (3-D rows >= 64): x += Par<c> * d * r  against numpy"""
+    import ctypes as C
+    host.set_mode(capi.MODE_EXACT)
+    dim = len(shape)
+    mb = host.MeshBuilder(dim).newMesh(*shape)
+    for d in range(dim):
+        mb.setMeshOfDim(d, 0., 1.)
+    mesh = mb.build()
+
+    def mk(name):
+        b = host.ExprBuilder().setMesh(mesh).setName(name).setLoc(loc).setExt(1)
+        for d in range(dim):
+            b.setBC(d, 0, host.BCType.Dirc, 0.).setBC(d, 1, host.BCType.Dirc, 0.)
+        return b.build()
+    x, dv, r = mk("x"), mk("d"), mk("r")
+    ar = x.assignableRange
+    shp = ar.shape(dim)
+    rs = np.random.RandomState(7)
+    X, D, R = (np.asfortranarray(rs.rand(*shp)) for _ in range(3))
+    idx = np.indices(shp).astype(np.int64)
+    gsum = sum(idx[d] + ar.start[d] for d in range(dim))
+    for c in (0, 1):
+        x.from_numpy(X, ar), dv.from_numpy(D, ar), r.from_numpy(R, ar)
+        F = (C.c_void_p * 3)(x.h, dv.h, r.h)
+        S = (C.c_double * 1)(0.0)
+        capi.check(capi.lib().opf_assign(x.h, 0, f"Add<F<0>,Mul<Par<{c}>,Mul<F<1>,F<2>>>>".encode(), F, 3, S, 0))
+        want = X + np.where((gsum & 1) == c, 1.0, 0.0) * (D * R)
+        assert np.array_equal(x.to_numpy(ar), want), f"colour {c}"
+    host.set_mode(capi.MODE_FAST)
