@@ -168,6 +168,11 @@ int opf_field_update_padding(opf_field_t f);
 int opf_field_set_bc_value(opf_field_t f, int axis, int pos, double value);
 /* std::swap(CartesianField&, CartesianField&) CartesianField.hpp:1039-1041: swaps storage only */
 int opf_field_swap(opf_field_t a, opf_field_t b);
+/* CartesianField::resplitWithStrategy (CartesianField.hpp:83-177): move a decomposed field, values kept, to the decomposition given by
+ * split_map (n_ranks cell-centred blocks like opf_field_desc.split_map).  Collective over the communicator; the handle stays valid, its
+ * ranges / neighbours / storage are those of a field built with the new map.  Solvers created on the field must be re-created.  Fields
+ * with functor boundary values are refused; a non-decomposed field is left alone (the reference's method only acts under MPI). */
+int opf_field_resplit(opf_field_t f, const opf_range* split_map);
 /* number of neighbours and their (rank, send, recv, shift-code) tuples: updateNeighbors :298-347 */
 int opf_field_neighbors(opf_field_t f, int cap, int* ranks, opf_range* send, opf_range* recv, int* codes);
 

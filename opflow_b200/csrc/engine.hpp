@@ -192,6 +192,9 @@ namespace opfe {
     int field_fill_bc(opf_field_s* f, const Range* clip, cudaStream_t st = nullptr);// steps 0-1 of updatePadding, optionally clipped to a box
     int field_fill_periodic(opf_field_s* f);// step 2 local part: periodic copies of the axes that are not split across ranks
     int field_ensure_twin(opf_field_s* f);
+    // f takes over g's decomposition, ranges and device storage; g is left without storage (the caller destroys it)
+    void field_adopt(opf_field_s* f, opf_field_s* g);
+    void repeat_cache_clear();// engine_expr.cu: captured opf_assign_repeat graphs hold buffer addresses
     // dense box (strides 1, d1, d2) <-> pitched storage of buffer `which` over range r, on stream st
     int dense_convert(opf_field_s* f, int which, double* dense, const Range& r, long long d1, long long d2, bool unpack, cudaStream_t st);
     int halo_exchange(opf_field_s* f, cudaStream_t st);// engine_comm.cu: pack, NCCL send/recv group, unpack -- all on `st`

@@ -211,6 +211,82 @@ int opf_comm_allreduce(double* values, int cnt, int rop) {
     return OPF_OK;
 }
 
+// CartesianField::resplitWithStrategy (CartesianField.hpp:83-177): the field keeps its values and moves to another decomposition.
+// Every rank sends  old localRange ∩ new block of r  to r and receives  new localRange ∩ old block of r  (dense boxes through one
+// staging buffer each way, one NCCL group), then takes over the storage planned for the new map and refreshes its padding.
+int opf_field_resplit(opf_field_t f, const opf_range* split_map) {
+    using namespace opfe;
+    if (!f || !split_map) return fail(OPF_ERR_INVALID, "opf_field_resplit: null argument");
+    if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
+    Nccl& n = nc();
+    if (f->n_ranks <= 1) return OPF_OK;// the reference's method only acts under MPI (:88)
+    if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
+    opf_field_desc d{};
+    d.mesh = f->mesh;
+    for (int a = 0; a < f->dim; ++a) {
+        d.loc[a] = f->loc[a];
+        for (int sd = 0; sd < 2; ++sd) {
+            if (f->bc[a][sd].face_dev) return fail(OPF_ERR_UNSUPPORTED, "opf_field_resplit: field '%s' has functor boundary values (their face slabs belong to the old blocks)", f->name.c_str());
+            d.bc[a][sd].type = f->bc[a][sd].type;
+            d.bc[a][sd].value = f->bc[a][sd].value;
+            d.bc[a][sd].face = nullptr;
+            d.ext[a][sd] = f->ext[a][sd];
+        }
+    }
+    d.padding = f->padding;
+    d.n_ranks = f->n_ranks;
+    d.rank = f->rank;
+    d.split_map = split_map;
+    opf_field_s* g = opf_field_create(&d, f->name.c_str());// collective: its first updatePadding exchanges (zero) halos
+    if (!g) return OPF_ERR_INVALID;
+    const int R = f->n_ranks, me = f->rank;
+    cudaStream_t st = ctx().stream;
+    std::vector<Range> sbox(R), rbox(R);
+    std::vector<long long> soff(R + 1, 0), roff(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        sbox[r] = common(f->local, g->split_map[r]);
+        rbox[r] = common(g->local, f->split_map[r]);
+        soff[r + 1] = soff[r] + std::max<long long>(0, sbox[r].count());
+        roff[r + 1] = roff[r] + std::max<long long>(0, rbox[r].count());
+    }
+    double *ss = nullptr, *rs = nullptr;
+    auto cleanup = [&](int rc) {
+        if (ss) cudaFree(ss);
+        if (rs) cudaFree(rs);
+        if (rc) opf_field_destroy(g);
+        return rc;
+    };
+    if (cudaMalloc(&ss, sizeof(double) * std::max<long long>(1, soff[R])) != cudaSuccess || cudaMalloc(&rs, sizeof(double) * std::max<long long>(1, roff[R])) != cudaSuccess)
+        return cleanup(fail(OPF_ERR_CUDA, "opf_field_resplit: staging allocation failed"));
+    auto dense = [&](opf_field_s* fld, const Range& r, double* stage, bool unpack) {
+        const long long n0 = r.end[0] - r.start[0], n1 = r.end[1] - r.start[1];
+        return dense_convert(fld, fld->cur, stage, r, n0, n0 * n1, unpack, st);
+    };
+    for (int r = 0; r < R; ++r)
+        if (sbox[r].count() > 0)
+            if (int rc = dense(f, sbox[r], ss + soff[r], false)) return cleanup(rc);
+    if (sbox[me].count() != rbox[me].count()) return cleanup(fail(OPF_ERR_INVALID, "opf_field_resplit: inconsistent self block"));
+    if (sbox[me].count() > 0)
+        if (cudaMemcpyAsync(rs + roff[me], ss + soff[me], sizeof(double) * sbox[me].count(), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return cleanup(fail(OPF_ERR_CUDA, "opf_field_resplit: local copy failed"));
+    if (n.GroupStart() != 0) return cleanup(fail(OPF_ERR_COMM, "ncclGroupStart failed"));
+    for (int r = 0; r < R; ++r) {
+        if (r == me) continue;
+        if (sbox[r].count() > 0 && n.Send(ss + soff[r], (size_t) sbox[r].count(), ncclFloat64, r, n.comm, st) != 0) return cleanup(fail(OPF_ERR_COMM, "ncclSend failed"));
+        if (rbox[r].count() > 0 && n.Recv(rs + roff[r], (size_t) rbox[r].count(), ncclFloat64, r, n.comm, st) != 0) return cleanup(fail(OPF_ERR_COMM, "ncclRecv failed"));
+    }
+    if (n.GroupEnd() != 0) return cleanup(fail(OPF_ERR_COMM, "ncclGroupEnd failed"));
+    for (int r = 0; r < R; ++r)
+        if (rbox[r].count() > 0)
+            if (int rc = dense(g, rbox[r], rs + roff[r], true)) return cleanup(rc);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return cleanup(fail(OPF_ERR_CUDA, "opf_field_resplit: exchange failed: %s", cudaGetErrorString(cudaGetLastError())));
+    cleanup(OPF_OK);
+    repeat_cache_clear();
+    field_adopt(f, g);
+    opf_field_destroy(g);
+    return field_update_padding(f);
+}
+
 int opf_comm_finalize(void) {
     Nccl& n = nc();
     if (n.comm) {

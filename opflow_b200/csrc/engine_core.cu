@@ -848,6 +848,19 @@ namespace opfe {
         f->buf[which] = nullptr;
     }
 
+    void field_adopt(opf_field_s* f, opf_field_s* g) {
+        for (int i = 0; i < 2; ++i) field_buf_free(f, i);
+        if (f->halo_send) cudaFree(f->halo_send);
+        if (f->halo_recv) cudaFree(f->halo_recv);
+        const std::string name = f->name;
+        *f = *g;// same mesh object: f keeps its own reference, g's is released when the caller destroys it
+        f->name = name;
+        g->buf[0] = g->buf[1] = nullptr;
+        g->halo_send = g->halo_recv = nullptr;
+        g->halo_elems = 0;
+        build_fill_program(f);// FillOps hold pointers to *this* field's BC objects
+    }
+
     int field_ensure_twin(opf_field_s* f) {
         if (f->buf[1 - f->cur]) return OPF_OK;
         OPF_CUDA(field_buf_alloc(f, 1 - f->cur));

@@ -1128,6 +1128,16 @@ namespace {
         return c;
     }
 }// namespace
+extern "C++" {
+namespace opfe {
+    void repeat_cache_clear() {
+        if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+        for (auto& e : repeat_cache())
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+        repeat_cache().clear();
+    }
+}// namespace opfe
+}
 int opf_assign_repeat(opf_field_t dst, int op, const char* signature, const opf_field_t* fields, int nfields, const double* scalars, int nscalars,
                       int count) {
     if (count < 0) return fail(OPF_ERR_INVALID, "negative repeat count");

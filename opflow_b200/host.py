@@ -332,6 +332,12 @@ class Field(Expr):
     def __imul__(self, e): return self.assign(e, OP_MUL)
     def __itruediv__(self, e): return self.assign(e, OP_DIV)
 
+    def resplit(self, split_map):
+        """CartesianField::resplitWithStrategy (CartesianField.hpp:83-177): split_map = the new strategy's cell-centred blocks, one per rank"""
+        arr = (Range * len(split_map))(*split_map)
+        check(lib().opf_field_resplit(self.h, arr))
+        return self
+
     def updatePadding(self):
         check(lib().opf_field_update_padding(self.h))
 

@@ -880,6 +880,30 @@ namespace OpFlow {
             touch();
             return *this;
         }
+        // resplitWithStrategy (CartesianField.hpp:83-177): values kept, blocks moved between the ranks.  Like the reference's it only
+        // acts on a decomposed run; the strategy itself is not stored (the reference keeps the builder's one as well).
+        template <typename S>
+        void resplitWithStrategy(S* strategy) {
+            if (!strategy || getWorkerCount() <= 1) return;
+            requireInit("resplitWithStrategy");
+            syncToDevice();
+            auto map = strategy->getSplitMap(mesh.getRange(), getGlobalParallelPlan());
+            std::vector<opf_range> split;
+            for (auto& r : map) split.push_back(internal::to_c(r));
+            internal::check_rc(opf_field_resplit(h, split.data()), "opf_field_resplit");
+            auto get = [&](int which) {
+                opf_range r;
+                internal::check_rc(opf_field_get_range(h, which, &r), "opf_field_get_range");
+                return internal::from_c<dim>(r);
+            };
+            localRange = get(0);
+            assignableRange = get(1);
+            accessibleRange = get(2);
+            logicalRange = get(3);
+            storageRange = get(4);
+            mirror.clear();
+            mirror_valid = host_dirty = false;
+        }
         void prepare() const {}
         const M& getMesh() const { return mesh; }
         auto getLocalWritableRange() const { return DS::commonRange(assignableRange, localRange); }

@@ -106,6 +106,16 @@ int main() {
         setGlobalParallelPlan(makeParallelPlan(getGlobalParallelInfo(), ParallelIdentifier::SharedMem));
     }
 
+    {// resplitWithStrategy (CartesianField.hpp:83-177) compiles against the reference's strategies; on one worker it leaves the field
+     // alone like the reference's method outside MPI (the move itself is checked on two GPUs by tests/mgpu_check.py)
+        auto before = u.localRange;
+        const Real v0 = u[DS::MDIndex<2> {u.assignableRange.start[0], u.assignableRange.start[1]}];
+        EvenSplitStrategy<Field> even;
+        u.resplitWithStrategy(&even);
+        CHECK(u.localRange.start[0] == before.start[0] && u.localRange.end[1] == before.end[1]);
+        CHECK((u[DS::MDIndex<2> {u.assignableRange.start[0], u.assignableRange.start[1]}] == v0));
+    }
+
     std::printf(failures ? "FAILED %d\n" : "PASS\n", failures);
     return failures ? 1 : 0;
 }
