@@ -914,8 +914,14 @@ namespace opf {
     // Thread <-> one cell of the fastest axes; the block marches along the slowest axis (chunk `ch` per block) so
     // that the planes/rows shared by consecutive iterations are served by L1 and loop-invariant per-axis
     // coefficient loads are hoisted.  Coalescing: axis 0 is contiguous across the warp.
+    // Many-operand expressions (the semi-implicit momentum operators: E::size > 48, the ones the register window is gated off for) are
+    // latency-bound at 128 registers per thread -- one 512-thread block, 24 % of the warps an SM can hold (profiles/r2_momentum_ncu.md).
+    // For them the kernel is compiled for three 256-thread blocks per SM (85 registers, ~1 KB of spill per thread): 9 % faster on the
+    // C5 momentum solves.  Everything else keeps the 512-thread / 128-register form (WENO, compound ops: FP64- or HBM-bound).
+    template <class E>
+    inline constexpr bool assign_many_operands = E::size > 48;
     template <class E, class P, bool A0, int DIM>
-    __global__ void __launch_bounds__(512) assign_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
+    __global__ void __launch_bounds__(assign_many_operands<E> ? 256 : 512, assign_many_operands<E> ? 3 : 1) assign_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
                                                          const double* __restrict__ oldp, const LaunchRange r,
                                                          const int ch, const int op) {
         const int i = r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1538,7 +1544,7 @@ namespace opf {
         while (tx > 32 && ((n0 + tx - 1) / tx) * tx - n0 > tx / 2) tx >>= 1;
         return tx;
     }
-    inline LaunchGeom assign_geometry(const LaunchInfo& li) {
+    inline LaunchGeom assign_geometry(const LaunchInfo& li, int max_threads = 512) {
         LaunchGeom g;
         const int n0 = li.r.hi[0] - li.r.lo[0], n1 = li.r.hi[1] - li.r.lo[1], n2 = li.r.hi[2] - li.r.lo[2];
         if (n0 <= 0 || n1 <= 0 || n2 <= 0) {
@@ -1562,7 +1568,8 @@ namespace opf {
             static const int ety = getenv("OPF_TY") ? atoi(getenv("OPF_TY")) : 0;
             static const int ech = getenv("OPF_CH") ? atoi(getenv("OPF_CH")) : 0;
             const int tx = etx > 0 ? etx : pick_tx(n0);
-            const int ty = ety > 0 ? ety : 4;
+            int ty = ety > 0 ? ety : 4;
+            while (ty > 1 && tx * ty > max_threads) ty >>= 1;
             g.block = dim3(tx, ty, 1);
             g.ch = ech > 0 ? ech : 32;
             g.grid = dim3((n0 + tx - 1) / tx, (n1 + ty - 1) / ty, (n2 + g.ch - 1) / g.ch);
@@ -1664,7 +1671,7 @@ namespace opf {
     // front-end knows its field's dimension at compile time and instantiates only that one)
     template <class E, class P, bool A0, int DIMS>
     int launch_assign(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
-        const LaunchGeom g = assign_geometry(li);
+        const LaunchGeom g = assign_geometry(li, assign_many_operands<E> ? 256 : 512);
         if (g.grid.x == 0) return 0;
         if constexpr (E::maxaxis < 1 && (DIMS & 1))
             if (li.dim == 1) {
@@ -1712,7 +1719,7 @@ namespace opf {
     // direct-global skeleton only (Stencil arithmetic: a verification mode, not a fast path)
     template <class E, class P, bool A0, int DIMS>
     int launch_assign_plain(const ExprArgs& a, const LaunchInfo& li, cudaStream_t st) {
-        const LaunchGeom g = assign_geometry(li);
+        const LaunchGeom g = assign_geometry(li, assign_many_operands<E> ? 256 : 512);
         if (g.grid.x == 0) return 0;
         opf_internal_note_kernel("opf::assign_kernel");
         if constexpr (E::maxaxis < 1 && (DIMS & 1))
