@@ -921,9 +921,8 @@ namespace opf {
     template <class E>
     inline constexpr bool assign_many_operands = E::size > 48;
     template <class E, class P, bool A0, int DIM>
-    __global__ void __launch_bounds__(assign_many_operands<E> ? 256 : 512, assign_many_operands<E> ? 3 : 1) assign_kernel(const __grid_constant__ ExprArgs a, const DstView dst,
-                                                         const double* __restrict__ oldp, const LaunchRange r,
-                                                         const int ch, const int op) {
+    __device__ __forceinline__ void assign_body(const ExprArgs& a, const DstView& dst, const double* __restrict__ oldp, const LaunchRange& r, const int ch,
+                                                const int op) {
         const int i = r.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= r.hi[0]) return;
         if constexpr (DIM == 1) {
@@ -953,6 +952,26 @@ namespace opf {
                 dst.p[o] = v;
             }
         }
+    }
+    // two compilations of the same body: the default one (512 threads, the compiler's own register choice) and the many-operand one
+    // (an explicit second launch-bounds argument also changes the register allocation of small kernels -- measured: + 18 % on the explicit
+    // corrections of C5 -- so it is not applied to them)
+    template <class E, class P, bool A0, int DIM>
+    __global__ void __launch_bounds__(512) assign_kernel(const __grid_constant__ ExprArgs a, const DstView dst, const double* __restrict__ oldp,
+                                                         const LaunchRange r, const int ch, const int op) {
+        assign_body<E, P, A0, DIM>(a, dst, oldp, r, ch, op);
+    }
+    template <class E, class P, bool A0, int DIM>
+    __global__ void __launch_bounds__(256, 3) assign_kernel_mo(const __grid_constant__ ExprArgs a, const DstView dst, const double* __restrict__ oldp,
+                                                               const LaunchRange r, const int ch, const int op) {
+        assign_body<E, P, A0, DIM>(a, dst, oldp, r, ch, op);
+    }
+    template <class E, class P, bool A0, int DIM, class G>
+    inline void launch_assign_kernel(const G& g, cudaStream_t st, const ExprArgs& a, const DstView& dst, const double* oldp, const LaunchRange& r,
+                                     int op) {
+        if constexpr (assign_many_operands<E>) assign_kernel_mo<E, P, A0, DIM><<<g.grid, g.block, 0, st>>>(a, dst, oldp, r, g.ch, op);
+        else
+            assign_kernel<E, P, A0, DIM><<<g.grid, g.block, 0, st>>>(a, dst, oldp, r, g.ch, op);
     }
 
     // ------------------------------------------------------------------------------------------- register-window skeleton
@@ -1675,7 +1694,7 @@ namespace opf {
         if (g.grid.x == 0) return 0;
         if constexpr (E::maxaxis < 1 && (DIMS & 1))
             if (li.dim == 1) {
-                assign_kernel<E, P, A0, 1><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                launch_assign_kernel<E, P, A0, 1>(g, st, a, li.dst, li.old, li.r, li.op);
                 opf_internal_note_kernel("opf::assign_kernel");
                 return (int) cudaGetLastError();
             }
@@ -1683,7 +1702,7 @@ namespace opf {
             if (li.dim == 2) {
                 if constexpr (WinInfo<E, A0, 2>::ok && E::nf > 0)
                     if (li.window) return launch_window<E, P, A0, 2>(a, li, st);
-                assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                launch_assign_kernel<E, P, A0, 2>(g, st, a, li.dst, li.old, li.r, li.op);
                 opf_internal_note_kernel("opf::assign_kernel");
                 return (int) cudaGetLastError();
             }
@@ -1710,7 +1729,7 @@ namespace opf {
                 }
                 if (li.window) return launch_window<E, P, A0, 3>(a, li, st);
             }
-            assign_kernel<E, P, A0, 3><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+            launch_assign_kernel<E, P, A0, 3>(g, st, a, li.dst, li.old, li.r, li.op);
             opf_internal_note_kernel("opf::assign_kernel");
             return (int) cudaGetLastError();
         }
@@ -1724,17 +1743,17 @@ namespace opf {
         opf_internal_note_kernel("opf::assign_kernel");
         if constexpr (E::maxaxis < 1 && (DIMS & 1))
             if (li.dim == 1) {
-                assign_kernel<E, P, A0, 1><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                launch_assign_kernel<E, P, A0, 1>(g, st, a, li.dst, li.old, li.r, li.op);
                 return (int) cudaGetLastError();
             }
         if constexpr (E::maxaxis < 2 && (DIMS & 2))
             if (li.dim == 2) {
-                assign_kernel<E, P, A0, 2><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                launch_assign_kernel<E, P, A0, 2>(g, st, a, li.dst, li.old, li.r, li.op);
                 return (int) cudaGetLastError();
             }
         if constexpr ((DIMS & 4) != 0)
             if (li.dim == 3) {
-                assign_kernel<E, P, A0, 3><<<g.grid, g.block, 0, st>>>(a, li.dst, li.old, li.r, g.ch, li.op);
+                launch_assign_kernel<E, P, A0, 3>(g, st, a, li.dst, li.old, li.r, li.op);
                 return (int) cudaGetLastError();
             }
         return -2;
