@@ -1,8 +1,8 @@
 #!/bin/bash
 # round 2p: final 1-GPU validation -- full GPU suite, default bench, C5, LidDriven2D timings, smoke
 cd /root/repo
-mkdir -p gpurun_out/r2p
-O=gpurun_out/r2p
+mkdir -p gpurun_out/r2r
+O=gpurun_out/r2r
 timeout 2400 python -m pytest tests -q -m gpu > $O/gputests.txt 2>&1
 tail -4 $O/gputests.txt
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_n1.json 2> $O/bench_n1.err
