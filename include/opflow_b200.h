@@ -275,8 +275,10 @@ typedef struct opf_solve_state { int niter; double relerr, abserr; } opf_solve_s
  * b = rhs - lhs(e = 0 with the real boundary data).  pin_value pins the first assignable cell exactly like the reference
  * (HYPREEqnSolveHandler.hpp:145-163, StencilField.hpp:132).  Supported: type PCG / BICGSTAB / GMRES(k) (FGMRES and LGMRES requests run as GMRES) / JACOBI / PFMG
  * (stand-alone geometric multigrid), precond NONE / JACOBI / PFMG.  lhs may also carry terms without the unknown (affine operator:
- * the front-end passes lhs(e) - rhs(e) with rhs "S<0>" = 0 when both sides of `==` contain e); multigrid needs an lhs whose field
- * leaves are all the unknown.  A decomposed target (opf_field_desc.split_map) is solved with distributed multigrid levels. */
+ * the front-end passes lhs(e) - rhs(e) with rhs "S<0>" = 0 when both sides of `==` contain e).  Multigrid on an lhs with coefficient
+ * fields restricts those fields level by level (one rank; constant boundary values; used when the level-0 diagonal does not dominate),
+ * otherwise such a request runs its level-0 smoother.  A decomposed target (opf_field_desc.split_map) with an lhs whose field leaves
+ * are all the unknown is solved with distributed multigrid levels. */
 opf_solver_t opf_solver_create(opf_field_t target, const char* lhs_signature, const opf_field_t* lhs_fields, int n_lhs_fields,
                                const double* lhs_scalars, int n_lhs_scalars, unsigned unknown_mask,
                                const opf_solver_params* params);
