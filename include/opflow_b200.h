@@ -173,6 +173,10 @@ int opf_field_swap(opf_field_t a, opf_field_t b);
  * ranges / neighbours / storage are those of a field built with the new map.  Solvers created on the field must be re-created.  Fields
  * with functor boundary values are refused; a non-decomposed field is left alone (the reference's method only acts under MPI). */
 int opf_field_resplit(opf_field_t f, const opf_range* split_map);
+/* the host half of opf_field_resplit, usable on a plan (no device): for this rank, the box it sends to and the box it receives from every
+ * rank r (send[r], recv[r]: n_ranks entries each, empty boxes where nothing moves; entry [rank] is the part that stays) and its
+ * localRange under the new map. */
+int opf_field_resplit_plan(opf_field_t f, const opf_range* split_map, opf_range* send, opf_range* recv, opf_range* new_local);
 /* number of neighbours and their (rank, send, recv, shift-code) tuples: updateNeighbors :298-347 */
 int opf_field_neighbors(opf_field_t f, int cap, int* ranks, opf_range* send, opf_range* recv, int* codes);
 

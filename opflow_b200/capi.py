@@ -129,6 +129,7 @@ SIGNATURES = {
     "opf_expr_builtin_name": (C.c_char_p, [C.c_int]),
     "opf_expr_prepare": (C.c_int, [C.c_char_p, C.POINTER(_V), C.c_int, C.c_int, _R, _I]),
     "opf_field_resplit": (C.c_int, [_V, C.POINTER(Range)]),
+    "opf_field_resplit_plan": (C.c_int, [_V, C.POINTER(Range), C.POINTER(Range), C.POINTER(Range), C.POINTER(Range)]),
     "opf_assign": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int]),
     "opf_assign_ex": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int]),
     "opf_assign_repeat": (C.c_int, [_V, C.c_int, C.c_char_p, C.POINTER(_V), C.c_int, _D, C.c_int, C.c_int]),

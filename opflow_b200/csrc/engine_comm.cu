@@ -214,19 +214,18 @@ int opf_comm_allreduce(double* values, int cnt, int rop) {
 // CartesianField::resplitWithStrategy (CartesianField.hpp:83-177): the field keeps its values and moves to another decomposition.
 // Every rank sends  old localRange ∩ new block of r  to r and receives  new localRange ∩ old block of r  (dense boxes through one
 // staging buffer each way, one NCCL group), then takes over the storage planned for the new map and refreshes its padding.
-int opf_field_resplit(opf_field_t f, const opf_range* split_map) {
+// the field the move ends in: same description as f, blocks from split_map (a device-free plan, or a field with storage)
+static opf_field_s* resplit_target(opf_field_s* f, const opf_range* split_map, bool plan_only) {
     using namespace opfe;
-    if (!f || !split_map) return fail(OPF_ERR_INVALID, "opf_field_resplit: null argument");
-    if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
-    Nccl& n = nc();
-    if (f->n_ranks <= 1) return OPF_OK;// the reference's method only acts under MPI (:88)
-    if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
     opf_field_desc d{};
     d.mesh = f->mesh;
     for (int a = 0; a < f->dim; ++a) {
         d.loc[a] = f->loc[a];
         for (int sd = 0; sd < 2; ++sd) {
-            if (f->bc[a][sd].face_dev) return fail(OPF_ERR_UNSUPPORTED, "opf_field_resplit: field '%s' has functor boundary values (their face slabs belong to the old blocks)", f->name.c_str());
+            if (f->bc[a][sd].face_dev || !f->bc[a][sd].face.empty()) {
+                fail(OPF_ERR_UNSUPPORTED, "opf_field_resplit: field '%s' has functor boundary values (their face slabs belong to the old blocks)", f->name.c_str());
+                return nullptr;
+            }
             d.bc[a][sd].type = f->bc[a][sd].type;
             d.bc[a][sd].value = f->bc[a][sd].value;
             d.bc[a][sd].face = nullptr;
@@ -237,15 +236,48 @@ int opf_field_resplit(opf_field_t f, const opf_range* split_map) {
     d.n_ranks = f->n_ranks;
     d.rank = f->rank;
     d.split_map = split_map;
-    opf_field_s* g = opf_field_create(&d, f->name.c_str());// collective: its first updatePadding exchanges (zero) halos
-    if (!g) return OPF_ERR_INVALID;
+    return plan_only ? opf_field_plan(&d, f->name.c_str()) : opf_field_create(&d, f->name.c_str());
+}
+// what rank `me` sends to / receives from every rank r:  old localRange ∩ new block of r  /  new localRange ∩ old block of r
+static void resplit_boxes(const opf_field_s* f, const opf_field_s* g, std::vector<opfe::Range>& sbox, std::vector<opfe::Range>& rbox) {
+    const int R = f->n_ranks;
+    sbox.assign(R, opfe::Range());
+    rbox.assign(R, opfe::Range());
+    for (int r = 0; r < R; ++r) {
+        sbox[r] = opfe::common(f->local, g->split_map[r]);
+        rbox[r] = opfe::common(g->local, f->split_map[r]);
+    }
+}
+
+int opf_field_resplit_plan(opf_field_t f, const opf_range* split_map, opf_range* send, opf_range* recv, opf_range* new_local) {
+    using namespace opfe;
+    if (!f || !split_map || !send || !recv) return fail(OPF_ERR_INVALID, "opf_field_resplit_plan: null argument");
+    if (f->n_ranks <= 1) return fail(OPF_ERR_INVALID, "opf_field_resplit_plan: field '%s' is not decomposed", f->name.c_str());
+    opf_field_s* g = resplit_target(f, split_map, true);
+    if (!g) return OPF_ERR_UNSUPPORTED;
+    std::vector<Range> sbox, rbox;
+    resplit_boxes(f, g, sbox, rbox);
+    for (int r = 0; r < f->n_ranks; ++r) send[r] = to_c(sbox[r]), recv[r] = to_c(rbox[r]);
+    if (new_local) *new_local = to_c(g->local);
+    opf_field_destroy(g);
+    return OPF_OK;
+}
+
+int opf_field_resplit(opf_field_t f, const opf_range* split_map) {
+    using namespace opfe;
+    if (!f || !split_map) return fail(OPF_ERR_INVALID, "opf_field_resplit: null argument");
+    if (!f->buf[0]) return fail(OPF_ERR_INVALID, "field '%s' is a plan (opf_field_plan): it has no device storage", f->name.c_str());
+    Nccl& n = nc();
+    if (f->n_ranks <= 1) return OPF_OK;// the reference's method only acts under MPI (:88)
+    if (!n.comm) return fail(OPF_ERR_COMM, "field '%s' is decomposed over %d ranks but opf_comm_init was not called", f->name.c_str(), f->n_ranks);
+    opf_field_s* g = resplit_target(f, split_map, false);// collective: its first updatePadding exchanges (zero) halos
+    if (!g) return OPF_ERR_UNSUPPORTED;
     const int R = f->n_ranks, me = f->rank;
     cudaStream_t st = ctx().stream;
-    std::vector<Range> sbox(R), rbox(R);
+    std::vector<Range> sbox, rbox;
+    resplit_boxes(f, g, sbox, rbox);
     std::vector<long long> soff(R + 1, 0), roff(R + 1, 0);
     for (int r = 0; r < R; ++r) {
-        sbox[r] = common(f->local, g->split_map[r]);
-        rbox[r] = common(g->local, f->split_map[r]);
         soff[r + 1] = soff[r] + std::max<long long>(0, sbox[r].count());
         roff[r + 1] = roff[r] + std::max<long long>(0, rbox[r].count());
     }

@@ -338,6 +338,14 @@ class Field(Expr):
         check(lib().opf_field_resplit(self.h, arr))
         return self
 
+    def resplit_plan(self, split_map):
+        """host half of resplit (works on a plan): -> (send boxes per rank, recv boxes per rank, new localRange)"""
+        n = len(split_map)
+        arr = (Range * n)(*split_map)
+        send, recv, nl = (Range * n)(), (Range * n)(), Range()
+        check(lib().opf_field_resplit_plan(self.h, arr, send, recv, C.byref(nl)))
+        return list(send), list(recv), nl
+
     def updatePadding(self):
         check(lib().opf_field_update_padding(self.h))
 

@@ -151,3 +151,106 @@ def test_slab_halo_plan_two_ranks(name):
         assert nnb >= 1 and checked > 0
     if CASES[name][1] is not None:  # periodic: both ranks see two neighbours (the seam links the last slab to the first)
         assert all(nnb == 2 for _, _, nnb in res)
+
+
+def _resplit_worker(rank, world, port, case, q):
+    """resplitWithStrategy's host half (opf_field_resplit_plan) on plan-only fields: every rank moves its block of the global function
+    to the new decomposition with gloo send/recv following the engine's send / recv boxes"""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dims, loc, new_axis = case
+        dim = len(dims)
+        mb = host.MeshBuilder(dim).newMesh(*dims)
+        for d in range(dim):
+            mb.setMeshOfDim(d, 0., 1.)
+        mesh = mb.build()
+        b = host.ExprBuilder().setName("u").setMesh(mesh).setLoc(loc)
+        for d in range(dim):
+            b.setBC(d, 0, host.BCType.Dirc, 1.).setBC(d, 1, host.BCType.Neum, 0.)
+        b.setPadding(1).setExt(1).setSplitStrategy(world, rank, host.split_slab(mesh, world))
+        u = b.plan()
+        lr = u.localRange
+        mr, _ = mesh.ranges()
+        ncell = mr.end[new_axis] - 1 - mr.start[new_axis]
+        new_map = []
+        for r_ in range(world):
+            st_, en_ = [mr.start[d] for d in range(3)], [mr.end[d] - 1 if d < dim else 1 for d in range(3)]
+            st_[new_axis] = mr.start[new_axis] + (ncell * r_) // world
+            en_[new_axis] = mr.start[new_axis] + (ncell * (r_ + 1)) // world
+            new_map.append(host.Range.make(st_, en_))
+        send, recv, nl = u.resplit_plan(new_map)
+
+        def glob(r):
+            grids = np.meshgrid(*[np.arange(r.start[d], r.end[d]) for d in range(dim)], indexing="ij")
+            gi = [grids[d] if d < dim else 0 for d in range(3)]
+            return _global(gi, dims)
+
+        def cnt(r):
+            return int(np.prod([max(0, r.end[d] - r.start[d]) for d in range(dim)]))
+
+        # what I send must be what the peer expects from me (box for box), and my send boxes partition my old block
+        allb = [None] * world
+        dist.all_gather_object(allb, ([s.tup(dim) for s in send], [r.tup(dim) for r in recv], lr.tup(dim), nl.tup(dim)))
+        for peer in range(world):
+            peer_expects = allb[peer][1][rank]
+            peer_cnt = int(np.prod([max(0, e - s) for s, e in zip(*peer_expects)]))
+            assert (cnt(send[peer]) == 0 and peer_cnt == 0) or send[peer].tup(dim) == peer_expects, (rank, peer)
+        assert sum(cnt(s) for s in send) == cnt(lr), "the send boxes do not cover the old block exactly once"
+        assert sum(cnt(r) for r in recv) == cnt(nl), "the recv boxes do not cover the new block exactly once"
+        old = glob(lr)
+        new = np.full([nl.end[d] - nl.start[d] for d in range(dim)], np.nan)
+        reqs, keep, got = [], [], []
+        for peer in range(world):
+            if cnt(send[peer]) and peer != rank:
+                sl = tuple(slice(send[peer].start[d] - lr.start[d], send[peer].end[d] - lr.start[d]) for d in range(dim))
+                t = torch.from_numpy(np.ascontiguousarray(old[sl]))
+                keep.append(t)
+                reqs.append(dist.isend(t, peer))
+            if cnt(recv[peer]) and peer != rank:
+                t = torch.empty([recv[peer].end[d] - recv[peer].start[d] for d in range(dim)], dtype=torch.float64)
+                reqs.append(dist.irecv(t, peer))
+                got.append((peer, t))
+        for rq in reqs:
+            rq.wait()
+        if cnt(send[rank]):
+            s_, r_ = send[rank], recv[rank]
+            assert s_.tup(dim) == r_.tup(dim)
+            new[tuple(slice(r_.start[d] - nl.start[d], r_.end[d] - nl.start[d]) for d in range(dim))] = \
+                old[tuple(slice(s_.start[d] - lr.start[d], s_.end[d] - lr.start[d]) for d in range(dim))]
+        for peer, t in got:
+            new[tuple(slice(recv[peer].start[d] - nl.start[d], recv[peer].end[d] - nl.start[d]) for d in range(dim))] = t.numpy()
+        assert np.array_equal(new, glob(nl)), "moved block differs from the global function"
+        # the new local range is what a field BUILT with the new map gets
+        b2 = host.ExprBuilder().setName("u2").setMesh(mesh).setLoc(loc)
+        for d in range(dim):
+            b2.setBC(d, 0, host.BCType.Dirc, 1.).setBC(d, 1, host.BCType.Neum, 0.)
+        b2.setPadding(1).setExt(1).setSplitStrategy(world, rank, new_map)
+        assert b2.plan().localRange.tup(dim) == nl.tup(dim)
+        q.put((rank, cnt(nl), sum(1 for p_ in range(world) if p_ != rank and cnt(send[p_]))))
+    finally:
+        dist.destroy_process_group()
+
+
+RESPLIT_CASES = {
+    "3d_corner_z_to_y": ((13, 17, 21), [0, 0, 0], 1),
+    "3d_center_z_to_x": ((13, 9, 17), [1, 1, 1], 0),
+    "2d_mac_y_to_x": ((21, 17), [0, 1], 0),
+}
+
+
+@pytest.mark.parametrize("name", list(RESPLIT_CASES))
+@pytest.mark.parametrize("world", [2, 3])
+def test_resplit_plan_moves_every_cell_once(name, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_resplit_worker, args=(r, world, port, RESPLIT_CASES[name], q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(n > 0 for _, n, _ in res)
+    assert all(peers == world - 1 for _, _, peers in res)  # a slab -> cross-slab move talks to every other rank
