@@ -1789,19 +1789,13 @@ static int run_pcg_device(opf_solver_s* s, const Range& w, double bnorm, double 
 }
 
 // one Krylov / stationary run on the current operator (s->pin_active), right-hand side s->B and iterate s->X
-// accept0 > 0: a starting iterate whose relative residual is <= accept0 is returned as it is (see the pinned phase of opf_solver_solve)
-static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm, double tol, int maxit, int* iters_io, double* rel_out,
-                         double accept0 = 0.0) {
+static int run_iteration(opf_solver_s* s, int type, const Range& w, double bnorm, double tol, int maxit, int* iters_io, double* rel_out) {
     auto& L0 = s->lv[0];
     double rnorm2 = 0;
     int iters = *iters_io;
     if (int rc = residual(s, s->X, s->B, s->R, s->Q, 0)) return rc;
     if (int rc = dot(s, s->R, s->R, w, &rnorm2)) return rc;
     double rel = std::sqrt(rnorm2) / bnorm;
-    if (accept0 > 0.0 && rel <= accept0) {
-        *rel_out = rel;
-        return OPF_OK;
-    }
     if (type == OPF_SOLVER_PCG && opf_internal_opt(OPF_OPT_FUSED_KRYLOV) && rel > tol && iters < maxit) {
         if (int rc = run_pcg_device(s, w, bnorm, tol, maxit, rnorm2, &iters, &rel)) return rc;
     } else if (type == OPF_SOLVER_PCG) {
@@ -2135,16 +2129,7 @@ int opf_solver_solve(opf_solver_t s, const char* rhs_signature, const opf_field_
         const int saved_pre = s->params.precond;
         s->params.precond = OPF_SOLVER_JACOBI;
         const int ptype = (type == OPF_SOLVER_PCG || type == OPF_SOLVER_PFMG || type == OPF_SOLVER_SMG || type == OPF_SOLVER_JACOBI) ? OPF_SOLVER_PCG : type;
-        // Phase 1 met the tolerance on the equivalent consistent system; the pinned system's residual of the shifted iterate differs
-        // from it by the rounding of the shift (x - x[pin] perturbs every difference by eps |x| / h^2: ~5e-11 of ||b|| on 4096^2 cells),
-        // which can land it a few per cent above tol.  Such an iterate is accepted (within OPF_PIN_ACCEPT x tol, default 4) instead of
-        // being handed to the Jacobi-preconditioned polish, which at the attainable-accuracy floor of a 1.7e7-unknown system wanders
-        // away from the solution rather than towards it (profiles/r2_summary.md section 8).  A b that really is inconsistent starts
-        // the polish far above that window and is treated as before.
-        static const double pin_accept = getenv("OPF_PIN_ACCEPT") ? atof(getenv("OPF_PIN_ACCEPT")) : 4.0;
-        static const double polish_tol_factor = getenv("OPF_PIN_POLISH_TOL_FACTOR") ? atof(getenv("OPF_PIN_POLISH_TOL_FACTOR")) : 1.0;// experiments
-        const double accept0 = (rel <= tol && pin_accept > 0) ? pin_accept * tol : 0.0;
-        int rc = run_iteration(s, ptype, w, bnorm, tol * polish_tol_factor, maxit, &iters, &rel, accept0 * polish_tol_factor);
+        int rc = run_iteration(s, ptype, w, bnorm, tol, maxit, &iters, &rel);
         s->params.precond = saved_pre;
         s->pin_active = false;
         return finish(rc);
